@@ -1,0 +1,71 @@
+/*
+ * qqq_b200.h — C ABI of libqqq_b200.so: the B200 (sm_100a) W4A8 GEMM behind QQQ's `qqq_gemm()` boundary.
+ *
+ * Every entry point takes raw device pointers, plain ints and a CUDA stream; none allocates, none
+ * synchronises, none touches torch.  Citations are into the reference tree (HandH1998/QQQ).
+ *
+ * Replaces:
+ *   csrc/qqq_gemm.cu:950-1046   int qqq_cuda(...)            -> qqq_gemm_sm100a()          (same argument list)
+ *   csrc/qqq_gemm.cu:1048-1106  void qqq_gemm(torch::Tensor…) -> python wrapper qqq_b200.ops.qqq_gemm over this ABI
+ *   csrc/pybind.cpp:3-5         QQQ._CUDA.qqq_gemm            -> see INTEGRATION.md for the two-line binding
+ *   QQQ/gptq/qlinear/qlinear_marlin.py:265-268 dynamic_quant  -> qqq_act_quant_sm100a()     (row "N2" of SURVEY §8f)
+ */
+#ifndef QQQ_B200_H_
+#define QQQ_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Return codes: 0 and 1/2 mirror ERR_PROB_SHAPE / ERR_KERN_SHAPE of csrc/qqq_gemm.cu:947-948. */
+#define QQQ_OK 0
+#define QQQ_ERR_PROB_SHAPE 1 /* (M,N,K,groupsize,thread_k,thread_n) not supported                       */
+#define QQQ_ERR_KERN_SHAPE 2 /* no kernel instantiation for the requested configuration                */
+#define QQQ_ERR_WORKSPACE 3  /* max_par too small for the scratch contract (see below)                 */
+#define QQQ_ERR_CUDA 4       /* a CUDA runtime/driver call failed; see qqq_b200_last_error()           */
+#define QQQ_ERR_DEVICE 5     /* device is not compute capability 10.x                                  */
+
+/*
+ * D[M,N] (fp16) = ((int32)(A[M,K] (int8) x W8[K,N]) * s2[n]) * s1[m]          csrc/qqq_gemm.cu:695-700
+ *   per-channel (groupsize == -1): W8 = nibble << 4 (= 16*w4), s2 = s_w/16     csrc/qqq_gemm.cu:146-151
+ *   per-group   (groupsize == 128): W8 = RNE((nibble-8) * s3[k/128][n])        csrc/qqq_gemm.cu:167-210
+ *
+ *   A   int8  [M,K] row-major                      B   int32 [K/16, 2N] reference ("Marlin") packing, untouched
+ *   C   int32 [>= 64*max_par, N] scratch           D   fp16  [M,N] row-major (written)
+ *   s1  fp32  [M]   per-token scales               s2  fp32  [N] per-channel scales, reference permutation
+ *   s3  fp16  [K/groupsize, N] reference permutation, or NULL/ignored when groupsize == -1
+ *   workspace int32 [>= N/128*max_par]
+ *
+ * Scratch contract (differs from the reference in ONE point): both `workspace` AND `C` must be all-zero on
+ * entry and are returned all-zero.  (The reference needs only `workspace` zeroed, csrc/qqq_gemm.cu:213-237;
+ * its QuantLinear allocates both with torch.zeros, qlinear_marlin.py:124-133, so module-level use is
+ * unchanged.)  C is used for split-K partial sums via integer atomics; results are order-independent.
+ *
+ * thread_k, thread_n, sms: -1 = auto.  thread_k/thread_n are validated like the reference
+ * (csrc/qqq_gemm.cu:867-916) and otherwise ignored: this kernel has its own tiling.  sms caps the grid.
+ * Alignment: A, B, D, s3 16-byte aligned; K % 128 == 0 and N % 64 == 0 (reference: (K%64,N%128)|(K%128,N%64)).
+ * The launch goes to `stream` on device `dev` (a device guard is applied; the reference has none).
+ */
+int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2,
+                    const void* s3, int prob_m, int prob_n, int prob_k, void* workspace, int groupsize,
+                    int dev, void* stream /* cudaStream_t */, int thread_k, int thread_n, int sms, int max_par);
+
+/*
+ * Per-token dynamic int8 quantisation of activations, bit-identical to
+ * QQQ/gptq/qlinear/qlinear_marlin.py:265-268:
+ *   s1[m] = fp32( fp16( max_k |x[m,k]| / 127 ) );   q[m,k] = int8( clamp( rint( x[m,k] / s1[m] ), -128, 127 ) )
+ *   x fp16 [M,K] row-major (K % 8 == 0, 16-byte aligned)  ->  q int8 [M,K], s1 fp32 [M]
+ */
+int qqq_act_quant_sm100a(const void* x, void* q, void* s1, int prob_m, int prob_k, int dev, void* stream);
+
+/* Library/ABI version (major*100 + minor) and the last error string of the calling thread. */
+int qqq_b200_version(void);
+const char* qqq_b200_last_error(void);
+
+/* Introspection used by bench.py / tests: number of kernel launches issued by this library so far. */
+long long qqq_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QQQ_B200_H_ */

@@ -152,12 +152,21 @@ def w8_per_group(nib: np.ndarray, s_group_nat: np.ndarray, group_size: int = 128
 # ----------------------------------------------------------------------------------------------------
 # Activation quantisation (qlinear_marlin.py:265-268)
 # ----------------------------------------------------------------------------------------------------
-def dynamic_quant(x: np.ndarray):
-    """x: fp16 [M, K].  scale = (absmax / 127) computed in fp16, then cast to fp32; x / scale is an fp32
-    division (fp16 / fp32 promotes), round-half-even, clamp, int8."""
+def dynamic_quant(x: np.ndarray, cuda_semantics: bool = True):
+    """x: fp16 [M, K].  scale = (absmax / 127) rounded to fp16, then cast to fp32; x / scale is an fp32
+    division (fp16 / fp32 promotes), round-half-even, clamp, int8.
+
+    `.div(127.0)` on an fp16 tensor: PyTorch's CUDA kernel multiplies by the fp32 reciprocal,
+    fp16(fp32(a) * fp32(1/127)) (ATen BinaryDivTrueKernel.cu, the "CPU scalar" fast path), while its CPU kernel
+    divides, fp16(fp32(a) / 127).  The reference only ever runs on CUDA, so cuda_semantics=True is the
+    contract; cuda_semantics=False reproduces the CPU-generated fixtures (tests/golden/pack_*.npz).  The two
+    differ only when the fp32 results straddle an fp16 rounding boundary."""
     x = x.astype(np.float16)
     amax = np.abs(x).max(axis=-1, keepdims=True)
-    scale = (amax / np.float16(127.0)).astype(np.float16).astype(np.float32)
+    if cuda_semantics:
+        scale = (amax.astype(np.float32) * np.float32(1.0 / 127.0)).astype(np.float16).astype(np.float32)
+    else:
+        scale = (amax.astype(np.float32) / np.float32(127.0)).astype(np.float16).astype(np.float32)
     with np.errstate(divide="ignore", invalid="ignore"):
         q = np.rint(x.astype(np.float32) / scale)
     q = np.clip(q, -128, 127)

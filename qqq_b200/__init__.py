@@ -1,0 +1,11 @@
+"""qqq_b200 — B200-native (sm_100a, tcgen05) W4A8 GEMM behind QQQ's `qqq_gemm()` / `QuantLinear` interface.
+
+Public surface (mirrors the reference hot path only):
+    qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k, thread_n, sms, max_par)   <- QQQ._CUDA.qqq_gemm
+    mul(...), QuantLinear (alias QQQLinear)                                          <- QQQ.gptq.qlinear
+"""
+from .ops import dynamic_quant, launch_count, qqq_gemm  # noqa: F401
+from .qlinear import QQQLinear, QuantLinear, mul, pack_int4_weights  # noqa: F401
+
+__all__ = ["qqq_gemm", "dynamic_quant", "mul", "QuantLinear", "QQQLinear", "pack_int4_weights", "launch_count"]
+__version__ = "0.1.0"

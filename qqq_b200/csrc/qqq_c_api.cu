@@ -1,0 +1,271 @@
+// C ABI of libqqq_b200.so (declared in include/qqq_b200.h): raw pointers + ints in, int rc out; no allocation,
+// no synchronisation, no torch.  Mirrors the shape of the reference's inner `qqq_cuda()` (csrc/qqq_gemm.cu:950-969).
+#include "../../include/qqq_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "qqq_common.cuh"
+#include "qqq_gemm_sm100.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      ok = false;
+      return;
+    }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+struct DeviceInfo {
+  bool valid = false;
+  int cc_major = 0;
+  int sms = 0;
+};
+DeviceInfo g_dev[64];
+std::mutex g_mu;
+
+const DeviceInfo* device_info(int dev) {
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_dev[dev].valid) {
+    int maj = 0, sms = 0;
+    if (cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return nullptr;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return nullptr;
+    g_dev[dev].cc_major = maj;
+    g_dev[dev].sms = sms;
+    g_dev[dev].valid = true;
+  }
+  return &g_dev[dev];
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency, so the
+// library still loads (and its symbols can be checked) on a machine without a GPU driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+bool encode_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t row_bytes,
+               uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_err("cuTensorMapEncodeTiled entry point unavailable");
+    return false;
+  }
+  cuuint64_t gdim[2] = {d0, d1};
+  cuuint64_t gstr[1] = {row_bytes};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err("cuTensorMapEncodeTiled failed (CUresult %d) dims=(%llu,%llu) box=(%u,%u)", (int)r,
+            (unsigned long long)d0, (unsigned long long)d1, b0, b1);
+    return false;
+  }
+  return true;
+}
+
+// The reference's tile-shape validity rule (csrc/qqq_gemm.cu:867-916), applied for error parity only.
+bool reference_shape_ok(int n, int k, int thread_k, int thread_n) {
+  static const int cfg[4][2] = {{128, 128}, {128, 64}, {64, 256}, {64, 128}};
+  if (thread_k != -1 && thread_n != -1) {
+    if (thread_k != 128 && thread_k != 64) return false;
+    if (thread_n < 64) return false;
+    return k % thread_k == 0 && n % thread_n == 0;
+  }
+  for (auto& c : cfg)
+    if (k % c[0] == 0 && n % c[1] == 0) return true;
+  return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qqq_b200_version(void) { return 100; }
+const char* qqq_b200_last_error(void) { return g_err; }
+long long qqq_b200_launch_count(void) { return g_launches.load(); }
+
+int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
+                    int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
+                    int thread_k, int thread_n, int sms, int max_par) {
+  using namespace qqq;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int M = prob_m, N = prob_n, K = prob_k;
+  if (M < 0 || N < 0 || K < 0) {
+    set_err("negative problem size");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  // reference: shape errors are reported before the empty-problem early-out (csrc/qqq_gemm.cu:996-1003)
+  if (!reference_shape_ok(N, K, thread_k, thread_n) || (groupsize != -1 && (groupsize <= 0 || K % groupsize != 0))) {
+    set_err("problem (m=%d, n=%d, k=%d) not compatible with thread_k=%d, thread_n=%d, groupsize=%d", M, N, K,
+            thread_k, thread_n, groupsize);
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  if (groupsize != -1 && groupsize != 128) {
+    // the reference instantiates group_blocks in {-1, 8} only (csrc/qqq_gemm.cu:935-945); QuantLinear passes a
+    // single group spanning K as the per-channel format (empty s3 -> groupsize -1)
+    set_err("groupsize %d not supported (only -1 and 128)", groupsize);
+    return QQQ_ERR_KERN_SHAPE;
+  }
+  if (M == 0 || N == 0 || K == 0) return QQQ_OK;
+  const bool grouped = groupsize == 128;
+  if (grouped && s3 == nullptr) {
+    set_err("s3 is null with groupsize=128");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  if (grouped && K % 128 != 0) {
+    set_err("per-group needs K %% 128 == 0");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(s3)) & 15) {
+    set_err("A, B and s3 must be 16-byte aligned");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  const DeviceInfo* di = device_info(dev);
+  if (!di) {
+    set_err("cannot query device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
+    return QQQ_ERR_CUDA;
+  }
+  if (di->cc_major != 10) {
+    set_err("device %d has compute capability %d.x; this library is sm_100a only", dev, di->cc_major);
+    return QQQ_ERR_DEVICE;
+  }
+  DeviceGuard guard(dev);
+  if (!guard.ok) {
+    set_err("cudaSetDevice(%d) failed", dev);
+    return QQQ_ERR_CUDA;
+  }
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = reinterpret_cast<int32_t*>(C);
+  p.D = reinterpret_cast<__half*>(D);
+  p.s1 = reinterpret_cast<const float*>(s1);
+  p.s2 = reinterpret_cast<const float*>(s2);
+  p.s3 = grouped ? reinterpret_cast<const __half*>(s3) : nullptr;
+  p.locks = reinterpret_cast<int*>(workspace);
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  // token tiling: the whole batch in one UMMA-N tile up to 256 tokens, otherwise equal tiles of <= 256
+  p.m_tiles = (M + kMaxTok - 1) / kMaxTok;
+  const int per_tile = (M + p.m_tiles - 1) / p.m_tiles;
+  p.n_tok = (per_tile + 15) / 16 * 16;
+  p.n_tiles = (N + kTileN - 1) / kTileN;
+  p.k_blocks = (K + kBlockK - 1) / kBlockK;
+  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  const long long units = tiles * p.k_blocks;
+  if (units >= (1ll << 31)) {
+    set_err("problem too large");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  p.total_units = (int)units;
+  const int stage_bytes = kStageB + p.n_tok * 128 + kStageS;
+  int ns = (kMaxSmemBytes - 1024 - 8 * (2 * kMaxStages + 2 * kASlots + 4) - 16) / stage_bytes;
+  if (ns > kMaxStages) ns = kMaxStages;
+  if (ns < 2) {
+    set_err("internal: no room for 2 pipeline stages");
+    return QQQ_ERR_KERN_SHAPE;
+  }
+  p.num_stages = ns;
+
+  int grid = (sms > 0 && sms < di->sms) ? sms : di->sms;
+  if ((long long)grid > units) grid = (int)units;
+  // split-K across CTAs needs the caller's scratch: C rows >= M (C has 64*max_par rows) and one lock per tile
+  const bool can_split = C != nullptr && workspace != nullptr && M <= 64 * max_par &&
+                         tiles <= (long long)(N / 128) * max_par;
+  if (can_split) {
+    p.units_per_cta = (int)((units + grid - 1) / grid);
+  } else {
+    const long long tiles_per_cta = (tiles + grid - 1) / grid;
+    p.units_per_cta = (int)(tiles_per_cta * p.k_blocks);
+  }
+  grid = (int)((units + p.units_per_cta - 1) / p.units_per_cta);
+  // weights are streamed once when a single token tile covers M; tokens are re-read by every CTA
+  p.hint_b = p.m_tiles == 1 ? kEvictFirst : kEvictNormal;
+  p.hint_a = kEvictLast;
+
+  CUtensorMap tmap_a, tmap_b;
+  if (!encode_2d(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, A, (uint64_t)K, (uint64_t)M, (uint64_t)K, kBlockK,
+                 (uint32_t)p.n_tok, CU_TENSOR_MAP_SWIZZLE_128B))
+    return QQQ_ERR_CUDA;
+  if (!encode_2d(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_INT32, B, (uint64_t)2 * N, (uint64_t)(K / 16), (uint64_t)N * 8,
+                 2 * kTileN, 8, CU_TENSOR_MAP_SWIZZLE_NONE))
+    return QQQ_ERR_CUDA;
+
+  cudaError_t e = launch_gemm(tmap_a, tmap_b, p, grouped, grid, dev, stream);
+  if (e != cudaSuccess) {
+    set_err("kernel launch failed: %s", cudaGetErrorString(e));
+    return QQQ_ERR_CUDA;
+  }
+  g_launches.fetch_add(1);
+  return QQQ_OK;
+}
+
+int qqq_act_quant_sm100a(const void* x, void* q, void* s1, int prob_m, int prob_k, int dev, void* stream_) {
+  if (prob_m < 0 || prob_k <= 0 || prob_k % 8 != 0) {
+    set_err("act_quant: K must be a positive multiple of 8 (got m=%d k=%d)", prob_m, prob_k);
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  if (prob_m == 0) return QQQ_OK;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(q) & 7)) {
+    set_err("act_quant: x must be 16-byte and q 8-byte aligned");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  const DeviceInfo* di = device_info(dev);
+  if (!di) {
+    set_err("cannot query device %d", dev);
+    return QQQ_ERR_CUDA;
+  }
+  if (di->cc_major != 10) {
+    set_err("device %d has compute capability %d.x; this library is sm_100a only", dev, di->cc_major);
+    return QQQ_ERR_DEVICE;
+  }
+  DeviceGuard guard(dev);
+  if (!guard.ok) return QQQ_ERR_CUDA;
+  cudaError_t e = qqq::launch_act_quant(x, q, s1, prob_m, prob_k, reinterpret_cast<cudaStream_t>(stream_));
+  if (e != cudaSuccess) {
+    set_err("act_quant launch failed: %s", cudaGetErrorString(e));
+    return QQQ_ERR_CUDA;
+  }
+  g_launches.fetch_add(1);
+  return QQQ_OK;
+}
+
+}  // extern "C"

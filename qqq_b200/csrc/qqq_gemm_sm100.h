@@ -1,0 +1,40 @@
+// Host/device shared declarations of the sm_100a W4A8 GEMM (see qqq_gemm_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace qqq {
+
+constexpr int kTileN = 128;      // output channels per CTA tile  (UMMA M)
+constexpr int kBlockK = 128;     // reduction depth per pipeline stage (= the per-group quantisation group)
+constexpr int kStageB = 8192;    // packed int4 bytes per stage: 8 rows of B x 256 words
+constexpr int kStageS = 256;     // group-scale bytes per stage: 128 channels x fp16
+constexpr int kASlots = 8;       // TMEM ring of unpacked int8 weight tiles (32 columns each)
+constexpr int kMaxStages = 16;
+constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
+constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+struct GemmParams {
+  int32_t* C;        // split-K partial sums [>= M rows, N], zero in / zero out
+  __half* D;         // output [M, N]
+  const float* s1;   // [M]
+  const float* s2;   // [N] permuted (reference scale_perm_single)
+  const __half* s3;  // [K/128, N] permuted (reference scale_perm) or nullptr
+  int* locks;        // [n_tiles * m_tiles] zero in / zero out
+  int M, N, K;
+  int n_tok;         // token tile, multiple of 16, <= 256
+  int m_tiles, n_tiles, k_blocks;
+  int num_stages;
+  int units_per_cta;  // stream-K: CTA b owns units [b*upc, (b+1)*upc); a unit = (tile, k-block), tile = mt + m_tiles*nt
+  int total_units;
+  uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
+};
+
+size_t gemm_smem_bytes(int num_stages, int n_tok);
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
+                        int grid, int dev, cudaStream_t stream);
+
+}  // namespace qqq

@@ -1,0 +1,95 @@
+"""Python face of the drop-in boundary: `qqq_gemm(...)` with the reference extension's exact signature
+(csrc/qqq_gemm.h:23-36, exported as QQQ._CUDA.qqq_gemm at csrc/pybind.cpp:3-5) and `dynamic_quant`
+(QQQ/gptq/qlinear/qlinear_marlin.py:265-268), both over the C ABI in include/qqq_b200.h.
+
+PyTorch is used only for device memory, dtypes and the current stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_ERR_PROB_SHAPE = 1
+_ERR_KERN_SHAPE = 2
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+def qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1, max_par=8):
+    """INT8 x INT4 -> FP16 GEMM.  Same 12 arguments, meaning and errors as the reference `qqq_gemm`
+    (csrc/qqq_gemm.cu:1048-1106):
+
+    A int8 [M,K]; B int32 [K/16, 2N] (reference packing); C int32 [>=64*max_par, N] scratch;
+    D fp16 [M,N] out; s1 fp32 [M,1]; s2 fp32 [1,N]; s3 fp16 [K/g, N] or empty; workspace int32
+    [>= N/128*max_par] zeros.  Raises RuntimeError on the same conditions the reference raises AT_ERROR.
+    N is taken from C.size(1) exactly like the reference (:1063).
+    """
+    prob_m = A.size(0)
+    prob_n = C.size(1)
+    prob_k = A.size(1)
+    groupsize = -1 if s3.numel() == 0 else prob_k // s3.size(0)
+    if groupsize != -1 and groupsize * s3.size(0) != prob_k:
+        raise RuntimeError(f"k={prob_k} not compatible with {s3.size(0)} groups.")
+    if workspace.numel() < prob_n // 128 * max_par:
+        raise RuntimeError(f"workspace must be of size at least {prob_n // 128 * max_par}.")
+    if s1.dtype != torch.float32:
+        raise RuntimeError(f"s1 dtype must be float32, but got {s1.dtype}.")
+    if s2.dtype != torch.float32:
+        raise RuntimeError(f"s2 dtype must be float32, but got {s2.dtype}.")
+    if s3.dtype != torch.float16:
+        raise RuntimeError(f"s3 dtype must be float16, but got {s3.dtype}.")
+    # Checks the reference omits (it would read garbage / fault instead): layout, dtype and device.
+    if not A.is_cuda:
+        raise RuntimeError("qqq_gemm: tensors must be CUDA tensors (qqq_b200 has no CPU path).")
+    for name, t, dt in (("A", A, torch.int8), ("B", B, torch.int32), ("C", C, torch.int32), ("D", D, torch.float16),
+                        ("workspace", workspace, torch.int32)):
+        if t.dtype != dt:
+            raise RuntimeError(f"{name} dtype must be {dt}, but got {t.dtype}.")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} must be contiguous.")
+        if t.device != A.device:
+            raise RuntimeError(f"{name} is on {t.device}, expected {A.device}.")
+    if C.size(0) < 64 * max_par and prob_m > 0:
+        raise RuntimeError(f"C must have at least {64 * max_par} rows.")
+    dev = A.get_device()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    lib = _lib.load()
+    err = lib.qqq_gemm_sm100a(
+        _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(s1), _ptr(s2), _ptr(s3) if s3.numel() else None,
+        prob_m, prob_n, prob_k, _ptr(workspace), groupsize, dev, stream, thread_k, thread_n, sms, max_par,
+    )
+    if err == _ERR_PROB_SHAPE:
+        raise RuntimeError(
+            f"Problem (m={prob_m}, n={prob_n}, k={prob_k}) not compatible with thread_k={thread_k}, thread_n={thread_n}."
+        )
+    if err == _ERR_KERN_SHAPE:
+        raise RuntimeError(
+            f"No kernel implementation for thread_k={thread_k}, thread_n={thread_n}, groupsize={groupsize}."
+        )
+    if err != 0:
+        raise RuntimeError(f"qqq_gemm_sm100a failed (rc={err}): {_lib.last_error()}")
+
+
+def dynamic_quant(x: torch.Tensor):
+    """Per-token int8 quantisation, bit-identical to the reference's 5 eager ops
+    (qlinear_marlin.py:265-268), as ONE kernel.  x fp16 [M,K] -> (int8 [M,K], fp32 [M,1])."""
+    if x.dtype != torch.float16 or not x.is_cuda:
+        raise RuntimeError("dynamic_quant expects a CUDA fp16 tensor (qqq_b200 has no CPU path).")
+    x = x.contiguous()
+    M, K = x.shape
+    q = torch.empty((M, K), dtype=torch.int8, device=x.device)
+    s = torch.empty((M, 1), dtype=torch.float32, device=x.device)
+    if M == 0:
+        return q, s
+    dev = x.get_device()
+    err = _lib.load().qqq_act_quant_sm100a(_ptr(x), _ptr(q), _ptr(s), M, K, dev, torch.cuda.current_stream(dev).cuda_stream)
+    if err != 0:
+        raise RuntimeError(f"qqq_act_quant_sm100a failed (rc={err}): {_lib.last_error()}")
+    return q, s
+
+
+def launch_count() -> int:
+    return int(_lib.load().qqq_b200_launch_count())
