@@ -2,9 +2,9 @@
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import qqq_oracle as O
-from tests.gpu_util import run_gemm, bits
+from gpu_util import run_gemm, bits
 
 for (M, K, N, gs) in [(16, 128, 128, -1), (16, 256, 128, -1), (1, 1024, 256, -1), (16, 128, 128, 128), (40, 2048, 384, 128), (300, 512, 256, -1), (20, 4096, 4096, -1)]:
     p = O.make_problem(M, K, N, gs, seed=1)

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import qqq_oracle as O
-from tests.gpu_util import bits, run_gemm
+from gpu_util import bits, run_gemm
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")

@@ -1,0 +1,89 @@
+"""CPU tests of the host-side mirror of the reference operator: QuantLinear ctor/buffers/pack()/state dict
+against the reference's own pack() outputs (tests/golden/pack_*.npz)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import qqq_b200
+from qqq_b200 import QuantLinear, pack_int4_weights
+from oracle import qqq_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PACK = sorted(glob.glob(os.path.join(GOLDEN, "pack_*.npz")))
+
+
+def _module_from_golden(g):
+    K, N, gs = int(g["K"]), int(g["N"]), int(g["group_size"])
+    lin = torch.nn.Linear(K, N, bias=True).half()
+    lin.weight.data = torch.from_numpy(g["weight_fq"]).clone()
+    lin.bias.data = torch.from_numpy(g["bias"]).clone()
+    ql = QuantLinear(4, gs, K, N, bias=True)
+    s_extra = torch.from_numpy(g["s_extra"]) if "s_extra" in g.files else None
+    ql.pack(lin, torch.from_numpy(g["scales"]), s_extra)
+    return ql
+
+
+@pytest.mark.parametrize("path", PACK, ids=os.path.basename)
+def test_pack_bit_identical_to_reference(path):
+    g = np.load(path)
+    ql = _module_from_golden(g)
+    assert np.array_equal(ql.B.numpy(), g["B"])
+    assert np.array_equal(ql.s_channel.numpy(), g["s_channel"])
+    assert np.array_equal(ql.s_group.numpy().view(np.uint16), g["s_group"].view(np.uint16))
+    assert np.array_equal(ql.bias.numpy().view(np.uint16), g["packed_bias"].view(np.uint16))
+    assert tuple(ql.workspace.shape) == tuple(g["workspace_shape"])
+    assert tuple(ql.reduce_buffer.shape) == tuple(g["reduce_buffer_shape"])
+    assert ql.B.dtype == torch.int32 and ql.s_channel.dtype == torch.float32 and ql.s_group.dtype == torch.float16
+    assert int(ql.workspace.abs().sum()) == 0 and int(ql.reduce_buffer.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("pg", [False, True])
+def test_vectorised_packer_equals_oracle_packer(pg):
+    rng = np.random.default_rng(7)
+    K, N = 160, 192
+    w = rng.integers(0, 16, (K, N)) if pg else rng.integers(-8, 8, (K, N))
+    assert np.array_equal(pack_int4_weights(torch.from_numpy(w), pg).numpy(), O.pack_B(w, pg))
+
+
+def test_state_dict_keys_and_roundtrip():
+    g = np.load(PACK[0])
+    ql = _module_from_golden(g)
+    sd = ql.state_dict()
+    assert set(sd.keys()) == {"B", "s_channel", "s_group", "bias"}  # workspace / reduce_buffer are non-persistent
+    K, N, gs = int(g["K"]), int(g["N"]), int(g["group_size"])
+    ql2 = QuantLinear(4, gs, K, N, bias=True)
+    ql2.load_state_dict(sd)
+    assert torch.equal(ql2.B, ql.B) and torch.equal(ql2.s_channel, ql.s_channel)
+
+
+def test_apply_pins_scale_dtypes():
+    ql = QuantLinear(4, 128, 256, 128, bias=False)
+    ql.half()
+    assert ql.s_channel.dtype == torch.float32 and ql.s_group.dtype == torch.float16
+    ql.float()
+    assert ql.s_channel.dtype == torch.float32 and ql.s_group.dtype == torch.float16
+
+
+def test_ctor_validation_matches_reference():
+    with pytest.raises(ValueError, match="Not supported `infeatures`"):
+        QuantLinear(4, -1, 100, 128, bias=False)
+    with pytest.raises(NotImplementedError, match="Only 4 bits"):
+        QuantLinear(8, -1, 128, 128, bias=False)
+    with pytest.raises(ValueError, match="Only group_size -1 and 128"):
+        QuantLinear(4, 64, 256, 128, bias=False)
+    with pytest.raises(NotImplementedError, match="does not support train"):
+        QuantLinear(4, -1, 128, 128, bias=False, trainable=True)
+    ql = QuantLinear(4, 256, 256, 128, bias=False)  # group_size == infeatures is the per-channel format
+    assert ql.s_group.numel() == 0 and ql.maxq == 7
+    assert QuantLinear(4, 128, 256, 128, bias=False).maxq == 15
+    assert qqq_b200.QQQLinear is QuantLinear
+
+
+def test_forward_without_gpu_fails_loudly():
+    """No CPU fallback: the product path raises instead of silently computing on the host."""
+    ql = QuantLinear(4, -1, 128, 128, bias=False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ql(torch.zeros(2, 128, dtype=torch.float16))
