@@ -1,0 +1,117 @@
+"""CPU, world_size=2, gloo: the tensor-parallel host logic (shard slicing of the packed tensors + the collectives).
+The per-rank GEMM is evaluated with the CPU oracle on the SHARD's buffers — exactly what the CUDA kernel is
+parity-tested against — so this checks that slicing B / s_channel / s_group needs no repack."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _full_module(p, K, N, gs):
+    import qqq_b200
+
+    ql = qqq_b200.QuantLinear(4, gs, K, N, bias=False)
+    ql.B.copy_(torch.from_numpy(p["B"]))
+    ql.s_channel.copy_(torch.from_numpy(p["s2"]))
+    if gs != -1:
+        ql.s_group.copy_(torch.from_numpy(p["s3"]))
+    return ql
+
+
+def _oracle_forward(ql, x_np):
+    from oracle import qqq_oracle as O
+
+    A8, s1 = O.dynamic_quant(x_np, cuda_semantics=True)
+    s3 = ql.s_group.numpy() if ql.s_group.numel() else None
+    return O.qqq_gemm_oracle(A8, ql.B.numpy(), s1, ql.s_channel.numpy(), s3)
+
+
+def _worker(rank, world, port, gs, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import qqq_oracle as O
+    from qqq_b200 import tp
+
+    M, K, N = 6, 512, 256
+    p = O.make_problem(M, K, N, gs, seed=11)
+    full = _full_module(p, K, N, gs)
+    D_full = _oracle_forward(full, p["x"])
+
+    # column parallel: shards are bit-identical column blocks of the 1-GPU result
+    col = tp.shard_quant_linear(full, rank, world, "column")
+    y_loc = torch.from_numpy(_oracle_forward(col, p["x"]))
+    parts = [torch.empty_like(y_loc) for _ in range(world)]
+    dist.all_gather(parts, y_loc)
+    D_col = torch.cat(parts, dim=1).numpy()
+    ok_col = np.array_equal(D_col.view(np.uint16), D_full.view(np.uint16))
+
+    # row parallel: per-shard activation scales + fp16 all-reduce => tolerance parity vs the full-K result
+    row = tp.shard_quant_linear(full, rank, world, "row")
+    _, offs = tp.split_sizes(K, world, 128 if gs != -1 else 64)
+    x_loc = p["x"][:, offs[rank]:offs[rank + 1]]
+    y_row = torch.from_numpy(_oracle_forward(row, x_loc)).float()
+    dist.all_reduce(y_row)
+    err_row = float(np.abs(y_row.numpy() - D_full.astype(np.float32)).max())
+    scale = float(np.abs(D_full.astype(np.float32)).max())
+
+    # exact mode: shared s1 (all-reduce-max of the row absmax) + int32 partial sums => bit-equal
+    amax = torch.from_numpy(np.abs(x_loc.astype(np.float32)).max(axis=1))
+    dist.all_reduce(amax, op=dist.ReduceOp.MAX)
+    A8_full, s1_full = O.dynamic_quant(p["x"], cuda_semantics=True)
+    s1_shared = (amax.numpy().astype(np.float16).astype(np.float32) * np.float32(1 / 127)).astype(np.float16).astype(np.float32)
+    ok_s1 = np.array_equal(s1_shared.reshape(-1, 1), s1_full)
+    A8_loc = A8_full[:, offs[rank]:offs[rank + 1]]
+    W8 = O.weights_int8(row.B.numpy(), row.s_group.numpy() if row.s_group.numel() else None)
+    acc = torch.from_numpy((A8_loc.astype(np.int64) @ W8.astype(np.int64)))
+    dist.all_reduce(acc)
+    W8f = O.weights_int8(full.B.numpy(), full.s_group.numpy() if full.s_group.numel() else None)
+    ok_acc = np.array_equal(acc.numpy(), A8_full.astype(np.int64) @ W8f.astype(np.int64))
+    if rank == 0:
+        out.put((ok_col, err_row, scale, ok_s1, ok_acc))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_tp2_sharding_gloo(gs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, gs, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = q.get(timeout=240)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    ok_col, err_row, scale, ok_s1, ok_acc = res
+    assert ok_col, "column-parallel shards must reproduce the 1-GPU columns bit-for-bit"
+    assert err_row <= 3e-2 * max(scale, 1.0), f"row-parallel error {err_row} vs scale {scale}"
+    assert ok_s1 and ok_acc, "exact row-parallel mode (shared s1 + int32 partials) must be bit-equal"
+
+
+def test_split_sizes():
+    from qqq_b200 import tp
+
+    sizes, offs = tp.split_sizes(11008, 8, 64)
+    assert sum(sizes) == 11008 and all(s % 64 == 0 for s in sizes) and max(sizes) - min(sizes) <= 64
+    assert offs[0] == 0 and offs[-1] == 11008
+    sizes, _ = tp.split_sizes(8192, 8, 128)
+    assert sizes == [1024] * 8
