@@ -345,11 +345,15 @@ def main():
     out_host = torch.empty(M, MODEL["hidden"], dtype=torch.float16).pin_memory()
     x_dev = x_host.to(dev)
 
-    # --- device-resident throughput (value) ---
+    # --- device-resident throughput (value): the 448 launches of a step are replayed from one CUDA graph ---
+    from qqq_b200 import graph as qgraph
+
     l0 = qqq_b200.launch_count()
+    forward_chain(layers, x_dev, world)
+    launches_per_step = qqq_b200.launch_count() - l0
+    graphed = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
     with ClockSampler(local_rank) as cs:
-        ms = timed(lambda: forward_chain(layers, x_dev, world), args.steps, args.warmup, barrier)
-    launches_per_step = (qqq_b200.launch_count() - l0) // (args.steps + args.warmup)
+        ms = timed(lambda: graphed(x_dev), args.steps, args.warmup, barrier)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -358,9 +362,15 @@ def main():
 
     # --- end to end: pinned host input -> H2D -> 224 linears -> D2H of the result, every step ---
     def e2e_step():
+        h = graphed(x_host)  # pinned host -> static device input (H2D), graph replay
+        out_host.copy_(h, non_blocking=True)  # D2H of the step's result
+
+    # the same step through the eager public API (no graph), for the record
+    def eager_step():
         x_dev.copy_(x_host, non_blocking=True)
-        h = forward_chain(layers, x_dev, world)
-        out_host.copy_(h, non_blocking=True)
+        out_host.copy_(forward_chain(layers, x_dev, world), non_blocking=True)
+
+    ms_eager = timed(eager_step, args.steps, args.warmup, barrier)
 
     ms_e2e = timed(e2e_step, args.steps, args.warmup, barrier)
     t = torch.tensor([ms_e2e], device=dev)
@@ -376,7 +386,12 @@ def main():
         if key not in qin:
             A8 = torch.randint(-127, 128, (M, key[0]), dtype=torch.int8, device=dev)
             qin[key] = (A8, torch.full((M, 1), 0.03, device=dev), torch.empty(M, key[1], dtype=torch.float16, device=dev))
-    ms_gemm = timed(lambda: gemm_only_chain(layers, qin), args.steps, args.warmup, barrier)
+    def _gemm_chain(x):
+        gemm_only_chain(layers, qin)
+        return x
+
+    graphed_gemm = qgraph.capture(_gemm_chain, x_dev)
+    ms_gemm = timed(lambda: graphed_gemm(x_dev), args.steps, args.warmup, barrier)
     n_gemm = MODEL["layers"] * len(LAYER_LINEARS)
     flops_rank = model_flops(M) / world
     int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
@@ -396,8 +411,11 @@ def main():
                     scaling="strong", vs_baseline=None, dtype="int8", data="synthetic", config=cfg,
                     clocks=cs.summary(),
                     e2e=dict(value=round(M / (ms_e2e * 1e-3), 1), unit="tokens/s", ms_per_step=round(ms_e2e, 4),
-                             h2d_bytes_per_step=x_host.numel() * 2, d2h_bytes_per_step=out_host.numel() * 2),
+                             h2d_bytes_per_step=x_host.numel() * 2, d2h_bytes_per_step=out_host.numel() * 2,
+                             api="qqq_b200.graph.capture(QuantLinear chain); eager QuantLinear.forward loop: "
+                                 f"{ms_eager:.3f} ms/step"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
+                    launch_mode="cuda-graph replay of the per-step launches",
                     roofline=roofline, tflops_linears=round(flops_rank * world / (ms * 1e-3) / 1e12, 1))
         if world == 1 and not args.no_sweep:
             line["gemm_sweep"] = gemm_sweep(dev, peaks)

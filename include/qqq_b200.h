@@ -36,10 +36,10 @@ extern "C" {
  *   s3  fp16  [K/groupsize, N] reference permutation, or NULL/ignored when groupsize == -1
  *   workspace int32 [>= N/128*max_par]
  *
- * Scratch contract (differs from the reference in ONE point): both `workspace` AND `C` must be all-zero on
- * entry and are returned all-zero.  (The reference needs only `workspace` zeroed, csrc/qqq_gemm.cu:213-237;
- * its QuantLinear allocates both with torch.zeros, qlinear_marlin.py:124-133, so module-level use is
- * unchanged.)  C is used for split-K partial sums via integer atomics; results are order-independent.
+ * Scratch contract (identical to the reference's): `workspace` must be all-zero on entry and is returned all-zero
+ * (csrc/qqq_gemm.cu:213-237); `C` is pure scratch (need not be zero, is not restored).  C holds split-K partial
+ * tiles: each contributing CTA stores its int32 partial into its own slot, the last arriver (lock word in
+ * `workspace`) sums the slots in a fixed order.  Results never depend on the partition or on arrival order.
  *
  * thread_k, thread_n, sms: -1 = auto.  thread_k/thread_n are validated like the reference
  * (csrc/qqq_gemm.cu:867-916) and otherwise ignored: this kernel has its own tiling.  sms caps the grid.

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "qqq_common.cuh"
 #include "qqq_gemm_sm100.h"
@@ -79,8 +80,49 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// Tensor maps depend only on (base pointer, dims, box): weights are long-lived module buffers and activation
+// buffers come back from the caching allocator, so a small cache removes the driver call from the hot path.
+struct MapKey {
+  const void* base;
+  uint64_t d0, d1;
+  uint32_t b0, b1, kind;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && b0 == o.b0 && b1 == o.b1 && kind == o.kind;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.d0 * 0xC2B2AE3D27D4EB4Full) ^ (k.d1 << 17) ^ ((uint64_t)k.b0 << 40) ^ ((uint64_t)k.b1 << 48) ^ k.kind;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+std::mutex g_maps_mu;
+
+bool encode_2d_uncached(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1,
+                        uint64_t row_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw);
+
 bool encode_2d(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t row_bytes,
                uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw) {
+  const MapKey key{base, d0, d1, b0, b1, (uint32_t)dt * 16u + (uint32_t)sw};
+  {
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *m = it->second;
+      return true;
+    }
+  }
+  if (!encode_2d_uncached(m, dt, base, d0, d1, row_bytes, b0, b1, sw)) return false;
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps.emplace(key, *m);
+  return true;
+}
+
+bool encode_2d_uncached(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1,
+                        uint64_t row_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) {
     set_err("cuTensorMapEncodeTiled entry point unavailable");
@@ -197,7 +239,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   }
   p.total_units = (int)units;
   const int stage_bytes = kStageB + p.n_tok * 128 + kStageS;
-  int ns = (kMaxSmemBytes - 1024 - 8 * (2 * kMaxStages + 2 * kASlots + 4) - 16) / stage_bytes;
+  int ns = (kMaxSmemBytes - 1024 - 8 * (2 * kMaxStages + 2 * kASlots + 4) - 16 - 4 * kMaxTok) / stage_bytes;
   if (ns > kMaxStages) ns = kMaxStages;
   if (ns < 2) {
     set_err("internal: no room for 2 pipeline stages");
@@ -207,13 +249,19 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
 
   int grid = (sms > 0 && sms < di->sms) ? sms : di->sms;
   if ((long long)grid > units) grid = (int)units;
-  // split-K across CTAs needs the caller's scratch: C rows >= M (C has 64*max_par rows) and one lock per tile
-  const bool can_split = C != nullptr && workspace != nullptr && M <= 64 * max_par &&
+  // Stream-K (a tile's k-range shared by several CTAs) needs one slot of C per contributor: C has 64*max_par rows,
+  // a slot is m_tiles*n_tok rows; and one lock word per tile.  Otherwise tiles are distributed whole.
+  const long long upc_split = (units + grid - 1) / grid;
+  const long long tiles_per_cta = (tiles + grid - 1) / grid;
+  const int parts_max = (upc_split % p.k_blocks == 0) ? 1 : (int)((p.k_blocks - 1) / upc_split) + 2;
+  const bool can_split = C != nullptr && workspace != nullptr &&
+                         (long long)parts_max * p.m_tiles * p.n_tok <= 64ll * max_par &&
                          tiles <= (long long)(N / 128) * max_par;
-  if (can_split) {
-    p.units_per_cta = (int)((units + grid - 1) / grid);
+  // splitting pays when whole-tile distribution would leave SMs idle for a noticeable part of the run
+  const double eff_whole = (double)tiles / (double)(tiles_per_cta * grid);
+  if (can_split && eff_whole < 0.92) {
+    p.units_per_cta = (int)upc_split;
   } else {
-    const long long tiles_per_cta = (tiles + grid - 1) / grid;
     p.units_per_cta = (int)(tiles_per_cta * p.k_blocks);
   }
   grid = (int)((units + p.units_per_cta - 1) / p.units_per_cta);

@@ -20,8 +20,9 @@
 //   4 epilogue warps  : tcgen05.ld -> fp32 scale by s2[n] then s1[m] (reference order, :695-700) -> fp16 -> D
 //
 // Scheduling: persistent CTAs, static stream-K over (tile, k-block) units.  A tile whose k-range is shared by
-// several CTAs is reduced with int32 atomics in `C` (order-independent, exact); the last CTA to arrive (lock
-// counter in `workspace`) applies the scales, writes D and restores C/lock to zero.
+// several CTAs is reduced through `C`: every contributor stores its int32 partial tile into its own slot (plain
+// coalesced stores), the last CTA to arrive (lock counter in `workspace`) sums the slots in a fixed order (exact,
+// deterministic), applies the scales, writes D and resets the lock.
 #include "qqq_common.cuh"
 #include "qqq_gemm_sm100.h"
 
@@ -101,6 +102,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t bar_dfull = bar_aempty + 8 * kASlots;
   const uint32_t bar_dempty = bar_dfull + 8 * 2;
   uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * kASlots + 4);  // [0] tmem base, [1] "last" flag
+  float* s1_sm = reinterpret_cast<float*>(misc + 4);                               // [kMaxTok] per-token scales
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.k_blocks;
@@ -133,12 +135,14 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      Ring st(NS);
-      for (int u = u_begin; u < u_end; ++u) {
-        const int tile = u / KB, kb = u - tile * KB;
-        const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
-        mbar_wait(bar_empty + 8 * st.idx, st.phase ^ 1);
+    // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected
+    // lane issues.
+    Ring st(NS);
+    for (int u = u_begin; u < u_end; ++u) {
+      const int tile = u / KB, kb = u - tile * KB;
+      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      mbar_wait(bar_empty + 8 * st.idx, st.phase ^ 1);
+      if (elect_one()) {
         const uint32_t full = bar_full + 8 * st.idx;
         uint32_t sbytes = 0;
         if (GROUPED) sbytes = (uint32_t)min(kTileN, p.N - nt * kTileN) * 2u;
@@ -147,41 +151,44 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         tma_load_2d(smem_u32(sT + st.idx * tok_bytes), &tmap_a, full, kb * kBlockK, mt * p.n_tok, p.hint_a);
         if (GROUPED)
           bulk_load_1d(smem_u32(sS + st.idx * kStageS), p.s3 + (size_t)kb * p.N + nt * kTileN, sbytes, full);
-        st.advance();
       }
+      __syncwarp();
+      st.advance();
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      Ring st(NS), as(kASlots);
-      const uint32_t idesc = make_idesc_i8(kTileN, p.n_tok);
-      int seg = 0;
-      for (int u = u_begin; u < u_end; ++seg) {
-        const int tile = u / KB, kb0 = u - tile * KB;
-        const int kb1 = min(KB, kb0 + (u_end - u));
-        const int dbuf = seg % ndbuf;
-        const uint32_t dph = (seg / ndbuf) & 1;
-        mbar_wait(bar_dempty + 8 * dbuf, dph ^ 1);
+    Ring st(NS), as(kASlots);
+    const uint32_t idesc = make_idesc_i8(kTileN, p.n_tok);
+    const uint64_t desc_tok0 = make_smem_desc(smem_u32(sT), 16, 1024, 2);
+    int seg = 0;
+    for (int u = u_begin; u < u_end; ++seg) {
+      const int tile = u / KB, kb0 = u - tile * KB;
+      const int kb1 = min(KB, kb0 + (u_end - u));
+      const int dbuf = seg % ndbuf;
+      const uint32_t dph = (seg / ndbuf) & 1;
+      mbar_wait(bar_dempty + 8 * dbuf, dph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + dbuf * p.n_tok;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_full + 8 * st.idx, st.phase);
+        mbar_wait(bar_afull + 8 * as.idx, as.phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + dbuf * p.n_tok;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_full + 8 * st.idx, st.phase);
-          mbar_wait(bar_afull + 8 * as.idx, as.phase);
-          tc_fence_after();
-          const uint32_t tok = smem_u32(sT + st.idx * tok_bytes);
+        if (elect_one()) {
+          const uint64_t desc = desc_tok0 + (uint64_t)((st.idx * tok_bytes) >> 4);
           const uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_i8_ts(tmem_d, tmem_a + ks * 8, make_smem_desc(tok + ks * 32, 16, 1024, 2), idesc,
-                       (kb > kb0 || ks > 0) ? 1u : 0u);
+            umma_i8_ts(tmem_d, tmem_a + ks * 8, desc + 2 * ks, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
           umma_commit(bar_empty + 8 * st.idx);
           umma_commit(bar_aempty + 8 * as.idx);
-          st.advance();
-          as.advance();
         }
-        umma_commit(bar_dfull + 8 * dbuf);
-        u += kb1 - kb0;
+        __syncwarp();
+        st.advance();
+        as.advance();
       }
+      if (elect_one()) umma_commit(bar_dfull + 8 * dbuf);
+      __syncwarp();
+      u += kb1 - kb0;
     }
   } else if (warp < kEpiWarp0) {
     // ===================================== unpack warps =====================================
@@ -240,7 +247,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================================== epilogue warps ===================================
     const int q = warp & 3;
     const int epi_tid = threadIdx.x - kEpiWarp0 * 32;
-    int seg = 0;
+    const int m_pad = p.m_tiles * p.n_tok;  // rows of one split-K slot in C
+    int seg = 0, staged_mt = -1;
     for (int u = u_begin; u < u_end; ++seg) {
       const int tile = u / KB, kb0 = u - tile * KB;
       const int kb1 = min(KB, kb0 + (u_end - u));
@@ -252,9 +260,20 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int m0 = mt * p.n_tok;
       const int rows = min(p.n_tok, p.M - m0);  // valid token rows of this tile
       const bool whole = (kb0 == 0 && kb1 == KB);
+      const int first_cta = (tile * KB) / p.units_per_cta;
+      const int parts = (tile * KB + KB - 1) / p.units_per_cta - first_cta + 1;
+      const int part = (int)blockIdx.x - first_cta;
       const float s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;
-      __half* dcol = p.D + n;
-      int* ccol = p.C + n;
+      __half* __restrict__ dcol = p.D + n;
+      int* __restrict__ ccol = p.C + n;
+
+      // per-token scales of this token tile -> smem (once per tile change), so the store loop has no global loads
+      if (mt != staged_mt) {
+        named_bar_sync(1, 128);  // previous users of s1_sm are done
+        for (int i = epi_tid; i < p.n_tok; i += 128) s1_sm[i] = (m0 + i < p.M) ? __ldg(p.s1 + m0 + i) : 0.f;
+        named_bar_sync(1, 128);
+        staged_mt = mt;
+      }
 
       mbar_wait(bar_dfull + 8 * dbuf, dph);
       tc_fence_after();
@@ -264,17 +283,21 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         tmem_ld_32x32b_x16(tmem_d + c16 * 16, r);
         tmem_wait_ld();
         if (n_ok) {
+          const int mb = c16 * 16;
+          if (whole) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int m = m0 + c16 * 16 + i;
-            if (m < p.M) {
-              if (whole) {
-                const float v = (__int2float_rn((int)r[i]) * s2v) * __ldg(p.s1 + m);
-                dcol[(size_t)m * p.N] = __float2half_rn(v);
-              } else if (r[i] != 0) {
-                atomicAdd(ccol + (size_t)m * p.N, (int)r[i]);
+            for (int i = 0; i < 16; ++i) {
+              if (mb + i < rows) {
+                const float v = (__int2float_rn((int)r[i]) * s2v) * s1_sm[mb + i];
+                dcol[(size_t)(m0 + mb + i) * p.N] = __float2half_rn(v);
               }
             }
+          } else {
+            // split-K: this CTA's partial sums go to its own slot of C (plain coalesced stores, no atomics)
+            int* __restrict__ slot = ccol + (size_t)(part * m_pad + m0 + mb) * p.N;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (mb + i < rows) slot[(size_t)i * p.N] = (int)r[i];
           }
         }
       }
@@ -283,10 +306,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       if (lane == 0) mbar_arrive(bar_dempty + 8 * dbuf);  // accumulator buffer may be overwritten
 
       if (!whole) {
-        // split-K fix-up: the last CTA to arrive finishes the tile and restores the scratch to zero
-        const int first_cta = (tile * KB) / p.units_per_cta;
-        const int last_cta = (tile * KB + KB - 1) / p.units_per_cta;
-        const int parts = last_cta - first_cta + 1;
+        // The last CTA to arrive on the tile's lock sums the slots in a fixed order (integer: exact), applies the
+        // scales, writes D and resets the lock.  C itself needs neither zeroing nor restoring.
         int* lock = p.locks + nt + p.n_tiles * mt;
         __threadfence();
         named_bar_sync(1, 128);
@@ -300,12 +321,10 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           __threadfence();
           if (n_ok) {
             for (int i = 0; i < rows; ++i) {
-              const int m = m0 + i;
-              int* cp = ccol + (size_t)m * p.N;
-              const int acc = __ldcg(cp);
-              const float v = (__int2float_rn(acc) * s2v) * __ldg(p.s1 + m);
-              dcol[(size_t)m * p.N] = __float2half_rn(v);
-              *cp = 0;
+              int acc = 0;
+              for (int pp = 0; pp < parts; ++pp) acc += __ldcg(ccol + (size_t)(pp * m_pad + m0 + i) * p.N);
+              const float v = (__int2float_rn(acc) * s2v) * s1_sm[i];
+              dcol[(size_t)(m0 + i) * p.N] = __float2half_rn(v);
             }
           }
           if (epi_tid == 0) *lock = 0;
@@ -324,7 +343,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 }  // namespace
 
 size_t gemm_smem_bytes(int num_stages, int n_tok) {
-  return 1024 + (size_t)num_stages * (kStageB + n_tok * 128 + kStageS) + 8 * (2 * num_stages + 2 * kASlots + 4) + 16;
+  return 1024 + (size_t)num_stages * (kStageB + n_tok * 128 + kStageS) + 8 * (2 * num_stages + 2 * kASlots + 4) + 16 +
+         4 * kMaxTok;
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,

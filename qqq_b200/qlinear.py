@@ -109,7 +109,7 @@ class QuantLinear(nn.Module):
             )
         else:
             self.register_buffer("s_group", torch.tensor([], dtype=torch.half))
-        # lock words / split-K partial sums: zero on entry, returned zeroed by the kernel (include/qqq_b200.h)
+        # lock words (zero in / zero out) and split-K scratch, same contract as the reference (include/qqq_b200.h)
         self.register_buffer("workspace", torch.zeros(outfeatures // 128 * 16, dtype=torch.int32), persistent=False)
         self.register_buffer(
             "reduce_buffer", torch.zeros((self.max_par * 16 * 4, outfeatures), dtype=torch.int), persistent=False

@@ -21,7 +21,7 @@ def test_bit_exact_vs_reference_kernel_fixture(path):
     p = {k: g[k] for k in ("A8", "B", "s1", "s2", "s3")}
     D, C, ws = run_gemm(p, int(g["N"]))
     assert np.array_equal(bits(D), bits(g["D"]))
-    assert int(C.abs().sum()) == 0 and int(ws.abs().sum()) == 0  # scratch restored
+    assert int(ws.abs().sum()) == 0  # lock words restored (C is scratch, like the reference's)
 
 
 CASES = [
@@ -42,7 +42,7 @@ def test_bit_exact_vs_oracle(M, K, N, gs):
     Dref = O.qqq_gemm_oracle(p["A8"], p["B"], p["s1"], p["s2"], p["s3"])
     nbad = int((bits(D) != bits(Dref)).sum())
     assert nbad == 0, f"{nbad}/{D.size} elements differ"
-    assert int(C.abs().sum()) == 0 and int(ws.abs().sum()) == 0
+    assert int(ws.abs().sum()) == 0
 
 
 @pytest.mark.parametrize("sms", [1, 3, 37, 148])
@@ -54,14 +54,17 @@ def test_split_k_partitions_are_exact(sms, gs):
     Dref = O.qqq_gemm_oracle(p["A8"], p["B"], p["s1"], p["s2"], p["s3"])
     D, C, ws = run_gemm(p, N, sms=sms)
     assert np.array_equal(bits(D), bits(Dref))
-    assert int(C.abs().sum()) == 0 and int(ws.abs().sum()) == 0
+    assert int(ws.abs().sum()) == 0
 
 
 def test_scratch_reuse_back_to_back():
-    """Same C/workspace for consecutive calls on one stream (how QuantLinear uses them)."""
+    """Same C/workspace for consecutive calls on one stream (how QuantLinear uses them); C may hold garbage
+    on entry, exactly like the reference's reduce buffer."""
     p1 = O.make_problem(8, 1024, 256, -1, seed=1)
     p2 = O.make_problem(40, 1024, 256, 128, seed=2)
-    D1, C, ws = run_gemm(p1, 256)
+    C0 = torch.randint(-2**31, 2**31 - 1, (16 * 64, 256), dtype=torch.int32, device="cuda:0")
+    ws0 = torch.zeros(64, dtype=torch.int32, device="cuda:0")
+    D1, C, ws = run_gemm(p1, 256, scratch=(C0, ws0))
     D2, C, ws = run_gemm(p2, 256, scratch=(C, ws))
     D1b, C, ws = run_gemm(p1, 256, scratch=(C, ws))
     assert np.array_equal(bits(D1), bits(D1b))
@@ -148,4 +151,4 @@ def test_full_size_sweep_shape_vs_int_mm(M, gs):
     acc = torch._int_mm(Ap, torch.from_numpy(W8.astype(np.int8)).to(dev))[:M]
     ref = ((acc.float() * torch.from_numpy(s2_nat).to(dev)[None, :]) * s1.to(dev)).half().cpu().numpy()
     assert np.array_equal(bits(D), bits(ref))
-    assert int(C.abs().sum()) == 0 and int(ws.abs().sum()) == 0
+    assert int(ws.abs().sum()) == 0
