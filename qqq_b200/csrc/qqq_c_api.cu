@@ -231,14 +231,19 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   p.n_tok = (per_tile + 15) / 16 * 16;
   p.n_tiles = (N + kTileN - 1) / kTileN;
   p.k_blocks = (K + kBlockK - 1) / kBlockK;
+  // decode-sized token tiles: several k-blocks per pipeline stage so that barrier round trips and the
+  // single-thread MMA issue loop are amortised over more weight bytes
+  p.ksub = p.n_tok <= 32 ? 4 : (p.n_tok <= 64 ? 2 : 1);
+  while (p.ksub > 1 && p.k_blocks < p.ksub) p.ksub >>= 1;
+  p.k_units = (p.k_blocks + p.ksub - 1) / p.ksub;
   const long long tiles = (long long)p.m_tiles * p.n_tiles;
-  const long long units = tiles * p.k_blocks;
+  const long long units = tiles * p.k_units;
   if (units >= (1ll << 31)) {
     set_err("problem too large");
     return QQQ_ERR_PROB_SHAPE;
   }
   p.total_units = (int)units;
-  const int stage_bytes = kStageB + p.n_tok * 128 + kStageS;
+  const int stage_bytes = p.ksub * (kStageB + p.n_tok * 128 + kStageS);
   int ns = (kMaxSmemBytes - 1024 - 8 * (2 * kMaxStages + 2 * kASlots + 4) - 16 - 4 * kMaxTok) / stage_bytes;
   if (ns > kMaxStages) ns = kMaxStages;
   if (ns < 2) {
@@ -253,7 +258,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   // a slot is m_tiles*n_tok rows; and one lock word per tile.  Otherwise tiles are distributed whole.
   const long long upc_split = (units + grid - 1) / grid;
   const long long tiles_per_cta = (tiles + grid - 1) / grid;
-  const int parts_max = (upc_split % p.k_blocks == 0) ? 1 : (int)((p.k_blocks - 1) / upc_split) + 2;
+  const int parts_max = (upc_split % p.k_units == 0) ? 1 : (int)((p.k_units - 1) / upc_split) + 2;
   const bool can_split = C != nullptr && workspace != nullptr &&
                          (long long)parts_max * p.m_tiles * p.n_tok <= 64ll * max_par &&
                          tiles <= (long long)(N / 128) * max_par;
@@ -262,7 +267,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   if (can_split && eff_whole < 0.92) {
     p.units_per_cta = (int)upc_split;
   } else {
-    p.units_per_cta = (int)(tiles_per_cta * p.k_blocks);
+    p.units_per_cta = (int)(tiles_per_cta * p.k_units);
   }
   grid = (int)((units + p.units_per_cta - 1) / p.units_per_cta);
   // weights are streamed once when a single token tile covers M; tokens are re-read by every CTA
@@ -274,7 +279,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
                  (uint32_t)p.n_tok, CU_TENSOR_MAP_SWIZZLE_128B))
     return QQQ_ERR_CUDA;
   if (!encode_2d(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_INT32, B, (uint64_t)2 * N, (uint64_t)(K / 16), (uint64_t)N * 8,
-                 2 * kTileN, 8, CU_TENSOR_MAP_SWIZZLE_NONE))
+                 2 * kTileN, 8 * p.ksub, CU_TENSOR_MAP_SWIZZLE_NONE))
     return QQQ_ERR_CUDA;
 
   cudaError_t e = launch_gemm(tmap_a, tmap_b, p, grouped, grid, dev, stream);

@@ -90,11 +90,13 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int NS = p.num_stages;
-  const int tok_bytes = p.n_tok * 128;
+  const int KSUB = p.ksub;                 // 128-deep k sub-blocks per pipeline stage ("unit")
+  const int tok_bytes = p.n_tok * 128;     // one sub-block of tokens
+  const int stage_b = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
   uint8_t* sB = smem;
-  uint8_t* sT = sB + NS * kStageB;
-  uint8_t* sS = sT + NS * tok_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NS * kStageS);
+  uint8_t* sT = sB + NS * stage_b;
+  uint8_t* sS = sT + NS * stage_t;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NS * stage_s);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * NS;
   const uint32_t bar_afull = bar_empty + 8 * NS;
@@ -105,7 +107,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   float* s1_sm = reinterpret_cast<float*>(misc + 4);                               // [kMaxTok] per-token scales
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = p.k_blocks;
+  const int KB = p.k_units;  // units (KSUB sub-blocks each) per tile
   const int u_begin = min((long long)blockIdx.x * p.units_per_cta, (long long)p.total_units);
   const int u_end = min((long long)u_begin + p.units_per_cta, (long long)p.total_units);
   const int ndbuf = p.n_tok <= 128 ? 2 : 1;
@@ -144,13 +146,22 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(bar_empty + 8 * st.idx, st.phase ^ 1);
       if (elect_one()) {
         const uint32_t full = bar_full + 8 * st.idx;
+        // k sub-blocks past the end of K are zero-filled by TMA (weights and tokens), so they add nothing
         uint32_t sbytes = 0;
-        if (GROUPED) sbytes = (uint32_t)min(kTileN, p.N - nt * kTileN) * 2u;
-        mbar_expect_tx(full, kStageB + tok_bytes + sbytes);
-        tma_load_2d(smem_u32(sB + st.idx * kStageB), &tmap_b, full, nt * (2 * kTileN), kb * 8, p.hint_b);
-        tma_load_2d(smem_u32(sT + st.idx * tok_bytes), &tmap_a, full, kb * kBlockK, mt * p.n_tok, p.hint_a);
-        if (GROUPED)
-          bulk_load_1d(smem_u32(sS + st.idx * kStageS), p.s3 + (size_t)kb * p.N + nt * kTileN, sbytes, full);
+        int nsub_valid = KSUB;
+        if (GROUPED) {
+          sbytes = (uint32_t)min(kTileN, p.N - nt * kTileN) * 2u;
+          nsub_valid = min(KSUB, p.k_blocks - kb * KSUB);
+        }
+        mbar_expect_tx(full, stage_b + stage_t + (GROUPED ? sbytes * nsub_valid : 0u));
+        tma_load_2d(smem_u32(sB + st.idx * stage_b), &tmap_b, full, nt * (2 * kTileN), kb * KSUB * 8, p.hint_b);
+        for (int sub = 0; sub < KSUB; ++sub) {
+          tma_load_2d(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, full, (kb * KSUB + sub) * kBlockK,
+                      mt * p.n_tok, p.hint_a);
+          if (GROUPED && sub < nsub_valid)
+            bulk_load_1d(smem_u32(sS + st.idx * stage_s + sub * kStageS),
+                         p.s3 + (size_t)(kb * KSUB + sub) * p.N + nt * kTileN, sbytes, full);
+        }
       }
       __syncwarp();
       st.advance();
@@ -159,7 +170,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================================== MMA issuer =======================================
     Ring st(NS), as(kASlots);
     const uint32_t idesc = make_idesc_i8(kTileN, p.n_tok);
-    const uint64_t desc_tok0 = make_smem_desc(smem_u32(sT), 16, 1024, 2);
+    const uint64_t desc_tok0 = make_smem_desc(smem_u32(sT), 16, 1024, 2);  // + byte offset >> 4 per stage / k-step
     int seg = 0;
     for (int u = u_begin; u < u_end; ++seg) {
       const int tile = u / KB, kb0 = u - tile * KB;
@@ -171,23 +182,27 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_full + 8 * st.idx, st.phase);
-        mbar_wait(bar_afull + 8 * as.idx, as.phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t desc = desc_tok0 + (uint64_t)((st.idx * tok_bytes) >> 4);
-          const uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32;
+        for (int sub = 0; sub < KSUB; ++sub) {
+          mbar_wait(bar_afull + 8 * as.idx, as.phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t desc = desc_tok0 + (uint64_t)((st.idx * stage_t + sub * tok_bytes) >> 4);
+            const uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_i8_ts(tmem_d, tmem_a + ks * 8, desc + 2 * ks, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
-          umma_commit(bar_empty + 8 * st.idx);
-          umma_commit(bar_aempty + 8 * as.idx);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_i8_ts(tmem_d, tmem_a + ks * 8, desc + 2 * ks, idesc, (kb > kb0 || sub > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(bar_aempty + 8 * as.idx);
+            if (sub == KSUB - 1) {
+              umma_commit(bar_empty + 8 * st.idx);
+              // same thread as the MMAs above: tcgen05.commit tracks the issuing thread's operations
+              if (kb == kb1 - 1) umma_commit(bar_dfull + 8 * dbuf);
+            }
+          }
+          __syncwarp();
+          as.advance();
         }
-        __syncwarp();
         st.advance();
-        as.advance();
       }
-      if (elect_one()) umma_commit(bar_dfull + 8 * dbuf);
-      __syncwarp();
       u += kb1 - kb0;
     }
   } else if (warp < kEpiWarp0) {
@@ -198,50 +213,53 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int q = warp & 3, nb = q >> 1, jp = q & 1;
     const int c = lane >> 2;
     Ring st(NS), as(kASlots);
-    int it = 0;
-    for (int u = u_begin; u < u_end; ++u, ++it) {
-      if ((it & 1) == grp) {
-        mbar_wait(bar_full + 8 * st.idx, st.phase);
-        mbar_wait(bar_aempty + 8 * as.idx, as.phase ^ 1);
-        tc_fence_after();
-        const uint8_t* src = sB + st.idx * kStageB + nb * 512 + lane * 16 + jp * 8;
-        uint2 w[8];
+    int it = 0;  // running sub-block index: the two groups take alternate sub-blocks
+    for (int u = u_begin; u < u_end; ++u) {
+      mbar_wait(bar_full + 8 * st.idx, st.phase);
+      for (int sub = 0; sub < KSUB; ++sub, ++it) {
+        if ((it & 1) == grp) {
+          mbar_wait(bar_aempty + 8 * as.idx, as.phase ^ 1);
+          tc_fence_after();
+          const uint8_t* src = sB + st.idx * stage_b + sub * kStageB + nb * 512 + lane * 16 + jp * 8;
+          uint2 w[8];
 #pragma unroll
-        for (int kt = 0; kt < 8; ++kt) w[kt] = *reinterpret_cast<const uint2*>(src + kt * 1024);
-        uint2 sc = make_uint2(0, 0);
-        if (GROUPED) sc = *reinterpret_cast<const uint2*>(sS + st.idx * kStageS + nb * 128 + c * 16 + jp * 8);
-        const uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32 + ((uint32_t)(32 * q) << 16);
+          for (int kt = 0; kt < 8; ++kt) w[kt] = *reinterpret_cast<const uint2*>(src + kt * 1024);
+          uint2 sc = make_uint2(0, 0);
+          if (GROUPED)
+            sc = *reinterpret_cast<const uint2*>(sS + st.idx * stage_s + sub * kStageS + nb * 128 + c * 16 + jp * 8);
+          const uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32 + ((uint32_t)(32 * q) << 16);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t s_b0 = 0, s_b1 = 0;
-          if (GROUPED) {
-            const uint32_t sp = h ? sc.y : sc.x;  // half2: (scale of channel c [blk0], scale of channel c+8 [blk1])
-            s_b0 = __byte_perm(sp, sp, 0x1010);
-            s_b1 = __byte_perm(sp, sp, 0x3232);
-          }
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            uint32_t r[8];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t word = h ? w[4 * part + g].y : w[4 * part + g].x;
-              if (GROUPED) {
-                r[2 * g] = unpack_pg4(word, s_b0);
-                r[2 * g + 1] = unpack_pg4(word >> 8, s_b1);
-              } else {
-                unpack_pc(word, r[2 * g], r[2 * g + 1]);
-              }
+          for (int h = 0; h < 2; ++h) {
+            uint32_t s_b0 = 0, s_b1 = 0;
+            if (GROUPED) {
+              const uint32_t sp = h ? sc.y : sc.x;  // half2: (scale of channel c [blk0], scale of channel c+8 [blk1])
+              s_b0 = __byte_perm(sp, sp, 0x1010);
+              s_b1 = __byte_perm(sp, sp, 0x3232);
             }
-            tmem_st_16x128b_x4(tmem_a + ((uint32_t)(16 * h) << 16) + part * 16, r);
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+              uint32_t r[8];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t word = h ? w[4 * part + g].y : w[4 * part + g].x;
+                if (GROUPED) {
+                  r[2 * g] = unpack_pg4(word, s_b0);
+                  r[2 * g + 1] = unpack_pg4(word >> 8, s_b1);
+                } else {
+                  unpack_pc(word, r[2 * g], r[2 * g + 1]);
+                }
+              }
+              tmem_st_16x128b_x4(tmem_a + ((uint32_t)(16 * h) << 16) + part * 16, r);
+            }
           }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_afull + 8 * as.idx);
         }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_afull + 8 * as.idx);
+        as.advance();
       }
       st.advance();
-      as.advance();
     }
   } else {
     // ===================================== epilogue warps ===================================
@@ -320,11 +338,23 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (last) {
           __threadfence();
           if (n_ok) {
-            for (int i = 0; i < rows; ++i) {
-              int acc = 0;
-              for (int pp = 0; pp < parts; ++pp) acc += __ldcg(ccol + (size_t)(pp * m_pad + m0 + i) * p.N);
-              const float v = (__int2float_rn(acc) * s2v) * s1_sm[i];
-              dcol[(size_t)(m0 + i) * p.N] = __float2half_rn(v);
+            for (int i0 = 0; i0 < rows; i0 += 16) {
+              int acc[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] = 0;
+              for (int pp = 0; pp < parts; ++pp) {
+                const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + i0) * p.N;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (i0 + j < rows) acc[j] += __ldcg(src + (size_t)j * p.N);
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (i0 + j < rows) {
+                  const float v = (__int2float_rn(acc[j]) * s2v) * s1_sm[i0 + j];
+                  dcol[(size_t)(m0 + i0 + j) * p.N] = __float2half_rn(v);
+                }
+              }
             }
           }
           if (epi_tid == 0) *lock = 0;
@@ -342,15 +372,15 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
 }  // namespace
 
-size_t gemm_smem_bytes(int num_stages, int n_tok) {
-  return 1024 + (size_t)num_stages * (kStageB + n_tok * 128 + kStageS) + 8 * (2 * num_stages + 2 * kASlots + 4) + 16 +
-         4 * kMaxTok;
+size_t gemm_smem_bytes(int num_stages, int n_tok, int ksub) {
+  return 1024 + (size_t)num_stages * ksub * (kStageB + n_tok * 128 + kStageS) + 8 * (2 * num_stages + 2 * kASlots + 4) +
+         16 + 4 * kMaxTok;
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream) {
   static bool attr_set[2][64] = {};  // the opt-in shared-memory attribute is per device
-  const size_t smem = gemm_smem_bytes(p.num_stages, p.n_tok);
+  const size_t smem = gemm_smem_bytes(p.num_stages, p.n_tok, p.ksub);
   auto kern = grouped ? qqq_gemm_kernel<true> : qqq_gemm_kernel<false>;
   if (dev < 0 || dev >= 64 || !attr_set[grouped][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);

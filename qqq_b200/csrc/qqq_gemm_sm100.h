@@ -27,13 +27,15 @@ struct GemmParams {
   int M, N, K;
   int n_tok;         // token tile, multiple of 16, <= 256
   int m_tiles, n_tiles, k_blocks;
+  int ksub;          // 128-deep k sub-blocks per pipeline stage (1, 2 or 4): amortises barrier traffic at small n_tok
+  int k_units;       // ceil(k_blocks / ksub): pipeline stages ("units") per tile
   int num_stages;
-  int units_per_cta;  // stream-K: CTA b owns units [b*upc, (b+1)*upc); a unit = (tile, k-block), tile = mt + m_tiles*nt
+  int units_per_cta;  // stream-K: CTA b owns units [b*upc, (b+1)*upc); a unit = (tile, k-unit), tile = mt + m_tiles*nt
   int total_units;
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
 };
 
-size_t gemm_smem_bytes(int num_stages, int n_tok);
+size_t gemm_smem_bytes(int num_stages, int n_tok, int ksub);
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream);
 
