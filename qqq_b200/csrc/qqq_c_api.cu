@@ -243,14 +243,23 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
     return QQQ_ERR_PROB_SHAPE;
   }
   p.total_units = (int)units;
-  const int stage_bytes = p.ksub * (kStageB + p.n_tok * 128 + kStageS);
-  int ns = (kMaxSmemBytes - 1024 - 8 * (2 * kMaxStages + 2 * kASlots + 4) - 16 - 4 * kMaxTok) / stage_bytes;
-  if (ns > kMaxStages) ns = kMaxStages;
-  if (ns < 2) {
-    set_err("internal: no room for 2 pipeline stages");
+  // smem rings: tokens get enough stages to cover L2 latency at the MMA's consumption rate (~128 KB in flight,
+  // 3..6 stages), the weight ring takes the rest (it is drained by the unpack warps, far ahead of the MMA)
+  const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
+  const int budget = kMaxSmemBytes - 1024 - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
+  int nst = (131072 + stage_t - 1) / stage_t;
+  nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
+  int nsw = 0;
+  for (; nst >= 2; --nst) {
+    nsw = (budget - nst * stage_t) / stage_w;
+    if (nsw >= 3) break;
+  }
+  if (nst < 2 || nsw < 2) {
+    set_err("internal: no room for the smem rings (n_tok=%d ksub=%d)", p.n_tok, p.ksub);
     return QQQ_ERR_KERN_SHAPE;
   }
-  p.num_stages = ns;
+  p.stages_t = nst;
+  p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
 
   int grid = (sms > 0 && sms < di->sms) ? sms : di->sms;
   if ((long long)grid > units) grid = (int)units;

@@ -5,21 +5,27 @@
 // 5th-gen tensor cores:
 //
 //   UMMA-M (128 TMEM lanes)  = 128 output channels of the weight tile
-//   UMMA-N (8..256 columns)  = the token tile (the whole batch at decode)
-//   UMMA-K = 32 int8, 4 per 128-deep k-block
+//   UMMA-N (16..256 columns) = the token tile (the whole batch at decode)
+//   UMMA-K = 32 int8, 4 per 128-deep k sub-block
 //
-//   TMA producer warp : packed int4 tile [8 x 1 KB] straight from the reference layout (B int32 [K/16,2N]),
-//                       int8 token tile [n_tok x 128 B] (128B swizzle), group scales row (per-group only)
-//   8 unpack warps    : LDS.64 packed words -> int8 (per-channel: 2 logic ops per word; per-group: exact
-//                       fp16 FMA rounding of the reference, csrc/qqq_gemm.cu:167-210) -> tcgen05.st.16x128b
-//                       into a TMEM ring.  The reference word layout (one word = 4 k x {n, n+8}) IS the
-//                       16x128b store fragment, so the weight tile becomes the UMMA A operand in TMEM
-//                       without any shuffle, shared-memory round trip or load-time repack.
-//   MMA warp (1 thr)  : tcgen05.mma.cta_group::1.kind::i8, A from TMEM, B (tokens) from smem descriptor,
-//                       int32 accumulators in TMEM (double-buffered when n_tok <= 128)
-//   4 epilogue warps  : tcgen05.ld -> fp32 scale by s2[n] then s1[m] (reference order, :695-700) -> fp16 -> D
+//   warp 0  weights producer : TMA of the packed int4 tile [8*KSUB rows x 1 KB] straight from the reference
+//                              layout (B int32 [K/16,2N]) + the group-scale rows (per-group only)  -> ring W
+//   warp 2  tokens producer  : TMA of the int8 token tile [n_tok x 128 B] (128B swizzle)           -> ring T
+//   12 unpack warps (3 groups of 4, one warp per TMEM lane quadrant): LDS.64 packed words -> int8 in registers
+//                              (per-channel: 2 logic ops per word; per-group: the reference's exact fp16-FMA
+//                              rounding, csrc/qqq_gemm.cu:167-210) -> tcgen05.st.16x128b into a TMEM ring.
+//                              The reference word layout (one word = 4 k x {n, n+8}) IS the 16x128b store
+//                              fragment, so the weight tile becomes the UMMA A operand in TMEM without any
+//                              shuffle, shared-memory round trip or load-time repack.
+//   warp 1  MMA issuer       : tcgen05.mma.cta_group::1.kind::i8, A from TMEM, B (tokens) from a smem descriptor,
+//                              int32 accumulators in TMEM (double-buffered when n_tok <= 128)
+//   4 epilogue warps         : tcgen05.ld -> fp32 * s2[n] * s1[m] (reference order, :695-700) -> fp16 -> D
 //
-// Scheduling: persistent CTAs, static stream-K over (tile, k-block) units.  A tile whose k-range is shared by
+// The two smem rings are decoupled: weight stages are released by the unpack warps as soon as they are in
+// registers, token stages by tcgen05.commit when the MMAs that read them retire; the TMEM ring lets the unpack
+// run several k-blocks ahead of the MMA.
+//
+// Scheduling: persistent CTAs, static stream-K over (tile, k-unit) units.  A tile whose k-range is shared by
 // several CTAs is reduced through `C`: every contributor stores its int32 partial tile into its own slot (plain
 // coalesced stores), the last CTA to arrive (lock counter in `workspace`) sums the slots in a fixed order (exact,
 // deterministic), applies the scales, writes D and resets the lock.
@@ -28,12 +34,22 @@
 
 namespace qqq {
 
-namespace {
+// Optional per-role timeline for development (probes/trace_timeline.py builds a separate library with -DQQQ_TRACE;
+// the product build compiles these hooks away).
+#ifdef QQQ_TRACE
+__device__ unsigned long long* g_trace = nullptr;  // [16 roles][2048 events] of clock64()
+#define QQQ_TR_INIT() unsigned long long* tr_ = (blockIdx.x == QQQ_TRACE_CTA) ? g_trace : nullptr
+#define QQQ_TR(role, idx)                                                            \
+  do {                                                                               \
+    const int i_ = (idx);                                                            \
+    if (tr_ != nullptr && i_ >= 0 && i_ < 2048) tr_[(role) * 2048 + i_] = clock64(); \
+  } while (0)
+#else
+#define QQQ_TR_INIT()
+#define QQQ_TR(role, idx)
+#endif
 
-constexpr int kThreads = 448;  // 14 warps: 0 TMA, 1 MMA, 2-9 unpack, 10-13 epilogue
-constexpr int kUnpackWarp0 = 2;
-constexpr int kEpiWarp0 = 10;
-constexpr int kTmemColsA0 = 256;  // A ring lives in columns [256, 512)
+namespace {
 
 struct Ring {
   int idx = 0;
@@ -44,6 +60,26 @@ struct Ring {
     if (++idx == n) {
       idx = 0;
       phase ^= 1;
+    }
+  }
+};
+
+// walks units u = (tile, k-unit) with tile = mt + m_tiles * nt, without divisions in the loop
+struct UnitIter {
+  int kb, mt, nt;
+  __device__ UnitIter(int u, int KU, int m_tiles) {
+    const int tile = u / KU;
+    kb = u - tile * KU;
+    nt = tile / m_tiles;
+    mt = tile - nt * m_tiles;
+  }
+  __device__ __forceinline__ void next(int KU, int m_tiles) {
+    if (++kb == KU) {
+      kb = 0;
+      if (++mt == m_tiles) {
+        mt = 0;
+        ++nt;
+      }
     }
   }
 };
@@ -89,38 +125,46 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int NS = p.num_stages;
-  const int KSUB = p.ksub;                 // 128-deep k sub-blocks per pipeline stage ("unit")
-  const int tok_bytes = p.n_tok * 128;     // one sub-block of tokens
-  const int stage_b = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
-  uint8_t* sB = smem;
-  uint8_t* sT = sB + NS * stage_b;
-  uint8_t* sS = sT + NS * stage_t;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NS * stage_s);
-  const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_empty = bar_full + 8 * NS;
-  const uint32_t bar_afull = bar_empty + 8 * NS;
-  const uint32_t bar_aempty = bar_afull + 8 * kASlots;
-  const uint32_t bar_dfull = bar_aempty + 8 * kASlots;
+  const int NSW = p.stages_w, NST = p.stages_t;
+  const int KSUB = p.ksub;                  // 128-deep k sub-blocks per pipeline stage ("unit")
+  const int NA = kASlotCols / (32 * KSUB);  // TMEM weight ring slots; one slot = one unit = 32*KSUB columns
+  const int tok_bytes = p.n_tok * 128;      // one sub-block of tokens
+  const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
+  uint8_t* sT = smem;
+  uint8_t* sW = sT + NST * stage_t;
+  uint8_t* sS = sW + NSW * stage_w;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSW * stage_s);
+  const uint32_t bar_fullw = smem_u32(bars);
+  const uint32_t bar_emptyw = bar_fullw + 8 * NSW;
+  const uint32_t bar_fullt = bar_emptyw + 8 * NSW;
+  const uint32_t bar_emptyt = bar_fullt + 8 * NST;
+  const uint32_t bar_afull = bar_emptyt + 8 * NST;
+  const uint32_t bar_aempty = bar_afull + 8 * kMaxASlots;
+  const uint32_t bar_dfull = bar_aempty + 8 * kMaxASlots;
   const uint32_t bar_dempty = bar_dfull + 8 * 2;
-  uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * kASlots + 4);  // [0] tmem base, [1] "last" flag
-  float* s1_sm = reinterpret_cast<float*>(misc + 4);                               // [kMaxTok] per-token scales
+  uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 2 * NSW + 2 * NST + 2 * kMaxASlots + 4);  // [0] tmem base, [1] flag
+  float* s1_sm = reinterpret_cast<float*>(misc + 4);                                            // [kMaxTok]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = p.k_units;  // units (KSUB sub-blocks each) per tile
+  const int KU = p.k_units;  // units per tile
   const int u_begin = min((long long)blockIdx.x * p.units_per_cta, (long long)p.total_units);
   const int u_end = min((long long)u_begin + p.units_per_cta, (long long)p.total_units);
   const int ndbuf = p.n_tok <= 128 ? 2 : 1;
+  QQQ_TR_INIT();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+    for (int i = 0; i < NSW; ++i) {
+      mbar_init(bar_fullw + 8 * i, 1);
+      mbar_init(bar_emptyw + 8 * i, 4 * KSUB);
     }
-    for (int i = 0; i < kASlots; ++i) {
-      mbar_init(bar_afull + 8 * i, 4);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(bar_fullt + 8 * i, 1);
+      mbar_init(bar_emptyt + 8 * i, 1);
+    }
+    for (int i = 0; i < kMaxASlots; ++i) {
+      mbar_init(bar_afull + 8 * i, 4 * KSUB);
       mbar_init(bar_aempty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -134,100 +178,130 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
+  if (threadIdx.x == 0) QQQ_TR(12, 0);
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== weights producer =================================
     // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected
-    // lane issues.
-    Ring st(NS);
+    // lane issues.  k sub-blocks past the end of K are zero-filled by TMA, so they add nothing.
+    Ring st(NSW);
+    UnitIter it(u_begin, KU, p.m_tiles);
     for (int u = u_begin; u < u_end; ++u) {
-      const int tile = u / KB, kb = u - tile * KB;
-      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
-      mbar_wait(bar_empty + 8 * st.idx, st.phase ^ 1);
+      mbar_wait(bar_emptyw + 8 * st.idx, st.phase ^ 1);
       if (elect_one()) {
-        const uint32_t full = bar_full + 8 * st.idx;
-        // k sub-blocks past the end of K are zero-filled by TMA (weights and tokens), so they add nothing
+        QQQ_TR(0, u - u_begin);
+        const uint32_t full = bar_fullw + 8 * st.idx;
         uint32_t sbytes = 0;
-        int nsub_valid = KSUB;
+        int nsub_valid = 0;
         if (GROUPED) {
-          sbytes = (uint32_t)min(kTileN, p.N - nt * kTileN) * 2u;
-          nsub_valid = min(KSUB, p.k_blocks - kb * KSUB);
+          sbytes = (uint32_t)min(kTileN, p.N - it.nt * kTileN) * 2u;
+          nsub_valid = min(KSUB, p.k_blocks - it.kb * KSUB);
         }
-        mbar_expect_tx(full, stage_b + stage_t + (GROUPED ? sbytes * nsub_valid : 0u));
-        tma_load_2d(smem_u32(sB + st.idx * stage_b), &tmap_b, full, nt * (2 * kTileN), kb * KSUB * 8, p.hint_b);
-        for (int sub = 0; sub < KSUB; ++sub) {
-          tma_load_2d(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, full, (kb * KSUB + sub) * kBlockK,
-                      mt * p.n_tok, p.hint_a);
-          if (GROUPED && sub < nsub_valid)
+        mbar_expect_tx(full, stage_w + sbytes * nsub_valid);
+        tma_load_2d(smem_u32(sW + st.idx * stage_w), &tmap_b, full, it.nt * (2 * kTileN), it.kb * KSUB * 8, p.hint_b);
+        if (GROUPED) {
+          for (int sub = 0; sub < nsub_valid; ++sub)
             bulk_load_1d(smem_u32(sS + st.idx * stage_s + sub * kStageS),
-                         p.s3 + (size_t)(kb * KSUB + sub) * p.N + nt * kTileN, sbytes, full);
+                         p.s3 + (size_t)(it.kb * KSUB + sub) * p.N + it.nt * kTileN, sbytes, full);
         }
+        QQQ_TR(1, u - u_begin);
       }
       __syncwarp();
       st.advance();
+      it.next(KU, p.m_tiles);
+    }
+  } else if (warp == 2) {
+    // ===================================== tokens producer ==================================
+    Ring st(NST);
+    UnitIter it(u_begin, KU, p.m_tiles);
+    for (int u = u_begin; u < u_end; ++u) {
+      mbar_wait(bar_emptyt + 8 * st.idx, st.phase ^ 1);
+      if (elect_one()) {
+        const uint32_t full = bar_fullt + 8 * st.idx;
+        mbar_expect_tx(full, stage_t);
+        for (int sub = 0; sub < KSUB; ++sub)
+          tma_load_2d(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, full, (it.kb * KSUB + sub) * kBlockK,
+                      it.mt * p.n_tok, p.hint_a);
+      }
+      __syncwarp();
+      st.advance();
+      it.next(KU, p.m_tiles);
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    Ring st(NS), as(kASlots);
+    Ring st(NST), as(NA);
     const uint32_t idesc = make_idesc_i8(kTileN, p.n_tok);
-    const uint64_t desc_tok0 = make_smem_desc(smem_u32(sT), 16, 1024, 2);  // + byte offset >> 4 per stage / k-step
+    const uint64_t desc_tok0 = make_smem_desc(smem_u32(sT), 16, 1024, 2);  // + (byte offset >> 4) per stage / k-step
     int seg = 0;
     for (int u = u_begin; u < u_end; ++seg) {
-      const int tile = u / KB, kb0 = u - tile * KB;
-      const int kb1 = min(KB, kb0 + (u_end - u));
+      const int tile = u / KU, kb0 = u - tile * KU;
+      const int kb1 = min(KU, kb0 + (u_end - u));
       const int dbuf = seg % ndbuf;
       const uint32_t dph = (seg / ndbuf) & 1;
       mbar_wait(bar_dempty + 8 * dbuf, dph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(bar_full + 8 * st.idx, st.phase);
-        for (int sub = 0; sub < KSUB; ++sub) {
-          mbar_wait(bar_afull + 8 * as.idx, as.phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t desc = desc_tok0 + (uint64_t)((st.idx * stage_t + sub * tok_bytes) >> 4);
-            const uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32;
+        mbar_wait(bar_fullt + 8 * st.idx, st.phase);
+        mbar_wait(bar_afull + 8 * as.idx, as.phase);
+        tc_fence_after();
+        if (elect_one()) {
+          QQQ_TR(5, u - u_begin + kb - kb0);
+          uint64_t desc = desc_tok0 + (uint64_t)((st.idx * stage_t) >> 4);
+          uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32 * KSUB;
+          for (int sub = 0; sub < KSUB; ++sub) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_i8_ts(tmem_d, tmem_a + ks * 8, desc + 2 * ks, idesc, (kb > kb0 || sub > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(bar_aempty + 8 * as.idx);
-            if (sub == KSUB - 1) {
-              umma_commit(bar_empty + 8 * st.idx);
-              // same thread as the MMAs above: tcgen05.commit tracks the issuing thread's operations
-              if (kb == kb1 - 1) umma_commit(bar_dfull + 8 * dbuf);
-            }
+            desc += (uint64_t)(tok_bytes >> 4);
+            tmem_a += 32;
           }
-          __syncwarp();
-          as.advance();
+          // same thread as the MMAs above: tcgen05.commit tracks the issuing thread's operations
+          umma_commit(bar_aempty + 8 * as.idx);
+          umma_commit(bar_emptyt + 8 * st.idx);
+          if (kb == kb1 - 1) umma_commit(bar_dfull + 8 * dbuf);
+          QQQ_TR(6, u - u_begin + kb - kb0);
         }
+        __syncwarp();
         st.advance();
+        as.advance();
       }
       u += kb1 - kb0;
     }
-  } else if (warp < kEpiWarp0) {
+  } else if (warp >= kUnpackWarp0 && warp < kEpiWarp0) {
     // ===================================== unpack warps =====================================
-    // Two groups of 4 warps alternate k-blocks; inside a group warp <-> TMEM lane quadrant q = warp % 4:
-    // channels [32q, 32q+32) of the tile = 64-channel block nb = q/2, 16-wide n-tiles j = 2(q%2) + {0,1}.
+    // Three groups of 4 warps take k sub-blocks round-robin; inside a group warp <-> TMEM lane quadrant
+    // q = warp % 4: channels [32q, 32q+32) of the tile = 64-channel block nb = q/2, 16-wide n-tiles j = 2(q%2)+{0,1}.
     const int grp = (warp - kUnpackWarp0) >> 2;
     const int q = warp & 3, nb = q >> 1, jp = q & 1;
     const int c = lane >> 2;
-    Ring st(NS), as(kASlots);
-    int it = 0;  // running sub-block index: the two groups take alternate sub-blocks
+    Ring st(NSW), as(NA);
+    int turn = 0;  // which group owns the next sub-block
+    int itn = 0;
     for (int u = u_begin; u < u_end; ++u) {
-      mbar_wait(bar_full + 8 * st.idx, st.phase);
-      for (int sub = 0; sub < KSUB; ++sub, ++it) {
-        if ((it & 1) == grp) {
-          mbar_wait(bar_aempty + 8 * as.idx, as.phase ^ 1);
-          tc_fence_after();
-          const uint8_t* src = sB + st.idx * stage_b + sub * kStageB + nb * 512 + lane * 16 + jp * 8;
+      bool stage_ready = false, slot_ready = false;
+      for (int sub = 0; sub < KSUB; ++sub, ++itn) {
+        if (turn == grp) {
+          if (!stage_ready) {
+            mbar_wait(bar_fullw + 8 * st.idx, st.phase);
+            stage_ready = true;
+          }
+          if (q == 0 && lane == 0) QQQ_TR(2, itn);
+          const uint8_t* src = sW + st.idx * stage_w + sub * kStageB + nb * 512 + lane * 16 + jp * 8;
           uint2 w[8];
 #pragma unroll
           for (int kt = 0; kt < 8; ++kt) w[kt] = *reinterpret_cast<const uint2*>(src + kt * 1024);
           uint2 sc = make_uint2(0, 0);
           if (GROUPED)
             sc = *reinterpret_cast<const uint2*>(sS + st.idx * stage_s + sub * kStageS + nb * 128 + c * 16 + jp * 8);
-          const uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32 + ((uint32_t)(32 * q) << 16);
+          if (!slot_ready) {  // the loads above are in flight while we wait for the TMEM slot
+            mbar_wait(bar_aempty + 8 * as.idx, as.phase ^ 1);
+            tc_fence_after();
+            slot_ready = true;
+          }
+          if (q == 0 && lane == 0) QQQ_TR(3, itn);
+          const uint32_t tmem_a =
+              tmem_base + kTmemColsA0 + as.idx * 32 * KSUB + sub * 32 + ((uint32_t)(32 * q) << 16);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t s_b0 = 0, s_b1 = 0;
@@ -252,34 +326,41 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               tmem_st_16x128b_x4(tmem_a + ((uint32_t)(16 * h) << 16) + part * 16, r);
             }
           }
+          if (q == 0 && lane == 0) QQQ_TR(10, itn);
           tmem_wait_st();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_afull + 8 * as.idx);
+          if (lane == 0) {
+            mbar_arrive(bar_afull + 8 * as.idx);
+            mbar_arrive(bar_emptyw + 8 * st.idx);  // this warp's reads of the weight stage are done
+          }
+          if (q == 0 && lane == 0) QQQ_TR(4, itn);
         }
-        as.advance();
+        turn = (turn == kUnpackGroups - 1) ? 0 : turn + 1;
       }
       st.advance();
+      as.advance();
     }
-  } else {
+  } else if (warp >= kEpiWarp0) {
     // ===================================== epilogue warps ===================================
     const int q = warp & 3;
     const int epi_tid = threadIdx.x - kEpiWarp0 * 32;
     const int m_pad = p.m_tiles * p.n_tok;  // rows of one split-K slot in C
+    const size_t ldn = (size_t)p.N;
     int seg = 0, staged_mt = -1;
     for (int u = u_begin; u < u_end; ++seg) {
-      const int tile = u / KB, kb0 = u - tile * KB;
-      const int kb1 = min(KB, kb0 + (u_end - u));
-      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      const int tile = u / KU, kb0 = u - tile * KU;
+      const int kb1 = min(KU, kb0 + (u_end - u));
+      const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
       const int dbuf = seg % ndbuf;
       const uint32_t dph = (seg / ndbuf) & 1;
       const int n = nt * kTileN + 32 * q + lane;
       const bool n_ok = n < p.N;
       const int m0 = mt * p.n_tok;
       const int rows = min(p.n_tok, p.M - m0);  // valid token rows of this tile
-      const bool whole = (kb0 == 0 && kb1 == KB);
-      const int first_cta = (tile * KB) / p.units_per_cta;
-      const int parts = (tile * KB + KB - 1) / p.units_per_cta - first_cta + 1;
+      const bool whole = (kb0 == 0 && kb1 == KU);
+      const int first_cta = (tile * KU) / p.units_per_cta;
+      const int parts = (tile * KU + KU - 1) / p.units_per_cta - first_cta + 1;
       const int part = (int)blockIdx.x - first_cta;
       const float s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;
       __half* __restrict__ dcol = p.D + n;
@@ -295,33 +376,50 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
       mbar_wait(bar_dfull + 8 * dbuf, dph);
       tc_fence_after();
+      if (epi_tid == 0) QQQ_TR(7, seg);
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok + ((uint32_t)(32 * q) << 16);
-      for (int c16 = 0; c16 * 16 < rows; ++c16) {
+      for (int mb = 0; mb < rows; mb += 16) {
         uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem_d + c16 * 16, r);
+        tmem_ld_32x32b_x16(tmem_d + mb, r);
         tmem_wait_ld();
-        if (n_ok) {
-          const int mb = c16 * 16;
-          if (whole) {
+        if (!n_ok) continue;
+        const bool full16 = mb + 16 <= rows;
+        if (whole) {
+          __half* __restrict__ dp = dcol + (size_t)(m0 + mb) * ldn;
+          const float4* s4 = reinterpret_cast<const float4*>(s1_sm + mb);
+          if (full16) {  // branch-free fast path
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (mb + i < rows) {
-                const float v = (__int2float_rn((int)r[i]) * s2v) * s1_sm[mb + i];
-                dcol[(size_t)(m0 + mb + i) * p.N] = __float2half_rn(v);
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 sv = s4[g4];
+              const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = 4 * g4 + j;
+                dp[(size_t)i * ldn] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]);
               }
             }
           } else {
-            // split-K: this CTA's partial sums go to its own slot of C (plain coalesced stores, no atomics)
-            int* __restrict__ slot = ccol + (size_t)(part * m_pad + m0 + mb) * p.N;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (mb + i < rows) slot[(size_t)i * p.N] = (int)r[i];
+              if (mb + i < rows) dp[(size_t)i * ldn] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * s1_sm[mb + i]);
+          }
+        } else {
+          // split-K: this CTA's partial sums go to its own slot of C (plain coalesced stores, no atomics)
+          int* __restrict__ slot = ccol + (size_t)(part * m_pad + m0 + mb) * ldn;
+          if (full16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) slot[(size_t)i * ldn] = (int)r[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (mb + i < rows) slot[(size_t)i * ldn] = (int)r[i];
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dempty + 8 * dbuf);  // accumulator buffer may be overwritten
+      if (epi_tid == 0) QQQ_TR(8, seg);
 
       if (!whole) {
         // The last CTA to arrive on the tile's lock sums the slots in a fixed order (integer: exact), applies the
@@ -343,44 +441,43 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 16; ++j) acc[j] = 0;
               for (int pp = 0; pp < parts; ++pp) {
-                const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + i0) * p.N;
+                const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + i0) * ldn;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                  if (i0 + j < rows) acc[j] += __ldcg(src + (size_t)j * p.N);
+                  if (i0 + j < rows) acc[j] += __ldcg(src + (size_t)j * ldn);
               }
+              __half* __restrict__ dp = dcol + (size_t)(m0 + i0) * ldn;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (i0 + j < rows) {
-                  const float v = (__int2float_rn(acc[j]) * s2v) * s1_sm[i0 + j];
-                  dcol[(size_t)(m0 + i0 + j) * p.N] = __float2half_rn(v);
-                }
-              }
+              for (int j = 0; j < 16; ++j)
+                if (i0 + j < rows) dp[(size_t)j * ldn] = __float2half_rn((__int2float_rn(acc[j]) * s2v) * s1_sm[i0 + j]);
             }
           }
           if (epi_tid == 0) *lock = 0;
         }
         named_bar_sync(1, 128);  // misc[1] is reused by the next segment
       }
+      if (epi_tid == 0) QQQ_TR(11, seg);
       u += kb1 - kb0;
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) QQQ_TR(12, 1);
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
 
-size_t gemm_smem_bytes(int num_stages, int n_tok, int ksub) {
-  return 1024 + (size_t)num_stages * ksub * (kStageB + n_tok * 128 + kStageS) + 8 * (2 * num_stages + 2 * kASlots + 4) +
-         16 + 4 * kMaxTok;
+size_t gemm_smem_bytes(const GemmParams& p) {
+  return 1024 + (size_t)p.stages_t * p.ksub * p.n_tok * 128 + (size_t)p.stages_w * p.ksub * (kStageB + kStageS) +
+         8 * (2 * p.stages_w + 2 * p.stages_t + 2 * kMaxASlots + 4) + 16 + 4 * kMaxTok;
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream) {
   static bool attr_set[2][64] = {};  // the opt-in shared-memory attribute is per device
-  const size_t smem = gemm_smem_bytes(p.num_stages, p.n_tok, p.ksub);
+  const size_t smem = gemm_smem_bytes(p);
   auto kern = grouped ? qqq_gemm_kernel<true> : qqq_gemm_kernel<false>;
   if (dev < 0 || dev >= 64 || !attr_set[grouped][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
@@ -390,5 +487,11 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, co
   kern<<<grid, kThreads, smem, stream>>>(tmap_a, tmap_b, p);
   return cudaGetLastError();
 }
+
+#ifdef QQQ_TRACE
+extern "C" int qqq_trace_set(void* buf) {
+  return (int)cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+}
+#endif
 
 }  // namespace qqq

@@ -9,13 +9,20 @@
 namespace qqq {
 
 constexpr int kTileN = 128;      // output channels per CTA tile  (UMMA M)
-constexpr int kBlockK = 128;     // reduction depth per pipeline stage (= the per-group quantisation group)
-constexpr int kStageB = 8192;    // packed int4 bytes per stage: 8 rows of B x 256 words
-constexpr int kStageS = 256;     // group-scale bytes per stage: 128 channels x fp16
-constexpr int kASlots = 8;       // TMEM ring of unpacked int8 weight tiles (32 columns each)
+constexpr int kBlockK = 128;     // reduction depth of one k sub-block (= the per-group quantisation group)
+constexpr int kStageB = 8192;    // packed int4 bytes per sub-block: 8 rows of B x 256 words
+constexpr int kStageS = 256;     // group-scale bytes per sub-block: 128 channels x fp16
+constexpr int kTmemColsA0 = 256; // TMEM: accumulators in columns [0,256), unpacked weight ring in [256,512)
+constexpr int kASlotCols = 256;
+constexpr int kMaxASlots = 8;    // ring slots of 32*ksub columns each
 constexpr int kMaxStages = 16;
 constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
 constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
+// warp roles: 0 weights TMA, 1 MMA (+TMEM alloc), 2 tokens TMA, 3 idle, 4-15 unpack (3 groups x 4), 16-19 epilogue
+constexpr int kUnpackWarp0 = 4;
+constexpr int kUnpackGroups = 3;
+constexpr int kEpiWarp0 = kUnpackWarp0 + 4 * kUnpackGroups;
+constexpr int kThreads = 32 * (kEpiWarp0 + 4);
 
 struct GemmParams {
   int32_t* C;        // split-K partial sums [>= M rows, N], zero in / zero out
@@ -29,13 +36,13 @@ struct GemmParams {
   int m_tiles, n_tiles, k_blocks;
   int ksub;          // 128-deep k sub-blocks per pipeline stage (1, 2 or 4): amortises barrier traffic at small n_tok
   int k_units;       // ceil(k_blocks / ksub): pipeline stages ("units") per tile
-  int num_stages;
+  int stages_w, stages_t;  // depth of the weight / token smem rings
   int units_per_cta;  // stream-K: CTA b owns units [b*upc, (b+1)*upc); a unit = (tile, k-unit), tile = mt + m_tiles*nt
   int total_units;
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
 };
 
-size_t gemm_smem_bytes(int num_stages, int n_tok, int ksub);
+size_t gemm_smem_bytes(const GemmParams& p);
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream);
 
