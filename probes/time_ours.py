@@ -55,6 +55,9 @@ def run(M, K, N, gs, graph=True):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "one":
+        run(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+        sys.exit(0)
     if which in ("all", "sweep"):
         for gs in (-1, 128):
             for M in (1, 16, 64, 128, 256, 1024, 4096):

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -231,9 +232,20 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   p.n_tok = (per_tile + 15) / 16 * 16;
   p.n_tiles = (N + kTileN - 1) / kTileN;
   p.k_blocks = (K + kBlockK - 1) / kBlockK;
-  // decode-sized token tiles: several k-blocks per pipeline stage so that barrier round trips and the
-  // single-thread MMA issue loop are amortised over more weight bytes
-  p.ksub = p.n_tok <= 32 ? 4 : (p.n_tok <= 64 ? 2 : 1);
+  // Tuning overrides for experiments (not part of the ABI): QQQ_B200_NTOK caps the token tile, QQQ_B200_KSUB /
+  // QQQ_B200_NST force the stage depth in k and the token ring depth.
+  static const int env_ntok = getenv("QQQ_B200_NTOK") ? atoi(getenv("QQQ_B200_NTOK")) : 0;
+  static const int env_ksub = getenv("QQQ_B200_KSUB") ? atoi(getenv("QQQ_B200_KSUB")) : 0;
+  static const int env_nst = getenv("QQQ_B200_NST") ? atoi(getenv("QQQ_B200_NST")) : 0;
+  if (env_ntok >= 16 && env_ntok <= kMaxTok && env_ntok % 16 == 0 && p.n_tok > env_ntok) {
+    p.m_tiles = (M + env_ntok - 1) / env_ntok;
+    const int pt = (M + p.m_tiles - 1) / p.m_tiles;
+    p.n_tok = (pt + 15) / 16 * 16;
+  }
+  // several k-blocks per pipeline stage so that barrier round trips and the single-thread MMA issue loop are
+  // amortised over >= 512 tensor-pipe cycles (an MMA of N tokens takes ~N/2 cycles, 4 per k-block)
+  p.ksub = p.n_tok <= 32 ? 4 : (p.n_tok <= 128 ? 2 : 1);
+  if (env_ksub == 1 || env_ksub == 2 || env_ksub == 4) p.ksub = env_ksub;
   while (p.ksub > 1 && p.k_blocks < p.ksub) p.ksub >>= 1;
   p.k_units = (p.k_blocks + p.ksub - 1) / p.ksub;
   const long long tiles = (long long)p.m_tiles * p.n_tiles;
@@ -249,6 +261,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   const int budget = kMaxSmemBytes - 1024 - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
   int nst = (131072 + stage_t - 1) / stage_t;
   nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
+  if (env_nst >= 2 && env_nst <= kMaxStages) nst = env_nst;
   int nsw = 0;
   for (; nst >= 2; --nst) {
     nsw = (budget - nst * stage_t) / stage_w;

@@ -436,6 +436,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (last) {
           __threadfence();
           if (n_ok) {
+            // all loads of a 16-row batch are issued before the first use (and the loop is unrolled twice),
+            // so a thread keeps up to 32*parts L2 requests in flight
+#pragma unroll 2
             for (int i0 = 0; i0 < rows; i0 += 16) {
               int acc[16];
 #pragma unroll
