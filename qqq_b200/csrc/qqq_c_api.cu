@@ -276,13 +276,13 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
 
   int grid = (sms > 0 && sms < di->sms) ? sms : di->sms;
   if ((long long)grid > units) grid = (int)units;
-  // Stream-K (a tile's k-range shared by several CTAs) needs one slot of C per contributor: C has 64*max_par rows,
-  // a slot is m_tiles*n_tok rows; and one lock word per tile.  Otherwise tiles are distributed whole.
+  // Stream-K (a tile's k-range shared by several CTAs) needs one slot of C per contributor but the last: C has
+  // 64*max_par rows, a slot is m_tiles*n_tok rows; and one lock word per tile.  Otherwise tiles are distributed whole.
   const long long upc_split = (units + grid - 1) / grid;
   const long long tiles_per_cta = (tiles + grid - 1) / grid;
   const int parts_max = (upc_split % p.k_units == 0) ? 1 : (int)((p.k_units - 1) / upc_split) + 2;
   const bool can_split = C != nullptr && workspace != nullptr &&
-                         (long long)parts_max * p.m_tiles * p.n_tok <= 64ll * max_par &&
+                         (long long)(parts_max - 1) * p.m_tiles * p.n_tok <= 64ll * max_par &&
                          tiles <= (long long)(N / 128) * max_par;
   // splitting pays when whole-tile distribution would leave SMs idle for a noticeable part of the run
   const double eff_whole = (double)tiles / (double)(tiles_per_cta * grid);

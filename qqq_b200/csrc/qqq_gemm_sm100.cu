@@ -378,13 +378,48 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       if (epi_tid == 0) QQQ_TR(7, seg);
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok + ((uint32_t)(32 * q) << 16);
+
+      // Split-K tiles: contributors take a ticket on the tile's lock word (low half = tickets, high half = partials
+      // published).  Tickets 0..parts-2 publish their int32 partial tile to slot[ticket] of C (plain coalesced
+      // stores); the last ticket keeps its partial in TMEM, waits until the others are published (they arrived
+      // earlier, so this is normally immediate), adds them and finishes the tile.  Integer sums: exact in any order.
+      int ticket = 0;
+      int* lock = p.locks + nt + p.n_tiles * mt;
+      if (!whole) {
+        named_bar_sync(1, 128);
+        if (epi_tid == 0) misc[1] = (uint32_t)atomicAdd(lock, 1) & 0xFFFFu;
+        named_bar_sync(1, 128);
+        ticket = (int)misc[1];
+        if (ticket == parts - 1) {
+          if (epi_tid == 0) {
+            while ((ld_acquire_gpu(lock) >> 16) != parts - 1) {
+            }
+          }
+          named_bar_sync(1, 128);
+          __threadfence();  // order this thread's reads of the published partials after the acquire above
+        }
+      }
+      const bool finish = whole || ticket == parts - 1;  // this CTA writes D for the tile
+      const int others = whole ? 0 : parts - 1;           // published partial tiles to add
+
       for (int mb = 0; mb < rows; mb += 16) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_d + mb, r);
         tmem_wait_ld();
         if (!n_ok) continue;
         const bool full16 = mb + 16 <= rows;
-        if (whole) {
+        if (finish) {
+          for (int pp = 0; pp < others; ++pp) {
+            const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + mb) * ldn;
+            if (full16) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) r[i] += (uint32_t)__ldcg(src + (size_t)i * ldn);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (mb + i < rows) r[i] += (uint32_t)__ldcg(src + (size_t)i * ldn);
+            }
+          }
           __half* __restrict__ dp = dcol + (size_t)(m0 + mb) * ldn;
           const float4* s4 = reinterpret_cast<const float4*>(s1_sm + mb);
           if (full16) {  // branch-free fast path
@@ -404,8 +439,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               if (mb + i < rows) dp[(size_t)i * ldn] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * s1_sm[mb + i]);
           }
         } else {
-          // split-K: this CTA's partial sums go to its own slot of C (plain coalesced stores, no atomics)
-          int* __restrict__ slot = ccol + (size_t)(part * m_pad + m0 + mb) * ldn;
+          int* __restrict__ slot = ccol + (size_t)(ticket * m_pad + m0 + mb) * ldn;
           if (full16) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) slot[(size_t)i * ldn] = (int)r[i];
@@ -422,42 +456,14 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       if (epi_tid == 0) QQQ_TR(8, seg);
 
       if (!whole) {
-        // The last CTA to arrive on the tile's lock sums the slots in a fixed order (integer: exact), applies the
-        // scales, writes D and resets the lock.  C itself needs neither zeroing nor restoring.
-        int* lock = p.locks + nt + p.n_tiles * mt;
-        __threadfence();
-        named_bar_sync(1, 128);
-        if (epi_tid == 0) {
-          const int old = atomicAdd(lock, 1);
-          misc[1] = (old == parts - 1) ? 1u : 0u;
-        }
-        named_bar_sync(1, 128);
-        const bool last = misc[1] != 0;
-        if (last) {
-          __threadfence();
-          if (n_ok) {
-            // all loads of a 16-row batch are issued before the first use (and the loop is unrolled twice),
-            // so a thread keeps up to 32*parts L2 requests in flight
-#pragma unroll 2
-            for (int i0 = 0; i0 < rows; i0 += 16) {
-              int acc[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] = 0;
-              for (int pp = 0; pp < parts; ++pp) {
-                const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + i0) * ldn;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (i0 + j < rows) acc[j] += __ldcg(src + (size_t)j * ldn);
-              }
-              __half* __restrict__ dp = dcol + (size_t)(m0 + i0) * ldn;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (i0 + j < rows) dp[(size_t)j * ldn] = __float2half_rn((__int2float_rn(acc[j]) * s2v) * s1_sm[i0 + j]);
-            }
-          }
+        if (finish) {
+          named_bar_sync(1, 128);  // every warp has read the published partials
           if (epi_tid == 0) *lock = 0;
+        } else {
+          __threadfence();  // partial tile visible device-wide before it is announced
+          named_bar_sync(1, 128);
+          if (epi_tid == 0) atomicAdd(lock, 0x10000);
         }
-        named_bar_sync(1, 128);  // misc[1] is reused by the next segment
       }
       if (epi_tid == 0) QQQ_TR(11, seg);
       u += kb1 - kb0;
