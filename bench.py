@@ -207,11 +207,32 @@ def timed(fn, steps, warmup, barrier):
 # ----------------------------------------------------------------------------------------------------------
 # GEMM sweep (configs[4])
 # ----------------------------------------------------------------------------------------------------------
+def graph_time_us(launch_all, n_launches, reps=3, warm=1):
+    """Time `launch_all()` (n_launches kernels back to back) replayed from a CUDA graph: device time per launch,
+    free of Python/ctypes launch cost."""
+    launch_all()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        launch_all()
+    for _ in range(warm):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * n_launches)
+
+
 def gemm_sweep(dev, peaks, quick=False):
+    """BASELINE configs[4]: M in {1,16,128,1024,4096}, K=8192, N=21760, per-channel and g128, vs fp16 cuBLAS."""
     import qqq_b200
 
     K, N = 8192, 21760
-    ncopy = 4  # 4 x 89 MB packed weights > 126 MB L2: every iteration streams from HBM
+    ncopy = 4  # 4 x 89 MB packed weights > 126 MB L2: every launch streams its weights from HBM
     g = torch.Generator(device=dev).manual_seed(0)
     Bs = [random_packed(K, N, g, dev) for _ in range(ncopy)]
     Wh = [torch.randn(K, N, dtype=torch.float16, device=dev) * 0.02 for _ in range(ncopy)]
@@ -220,7 +241,7 @@ def gemm_sweep(dev, peaks, quick=False):
     s3e = torch.zeros(0, dtype=torch.float16, device=dev)
     C = torch.zeros(16 * 64, N, dtype=torch.int32, device=dev)
     ws = torch.zeros(N // 128 * 16, dtype=torch.int32, device=dev)
-    int8_peak = 2.0 * peaks["bf16_tflops"]  # burst figure: each GEMM is timed alone
+    int8_peak = 2.0 * peaks["bf16_tflops"]  # burst figure: each GEMM is timed on its own
     out = []
     for M in ((1, 16, 128, 1024, 4096) if not quick else (16, 1024)):
         A = torch.randint(-127, 128, (M, K), dtype=torch.int8, device=dev)
@@ -228,27 +249,26 @@ def gemm_sweep(dev, peaks, quick=False):
         s1 = torch.rand(M, 1, device=dev) * 1e-2 + 1e-3
         D = torch.empty(M, N, dtype=torch.float16, device=dev)
         Dh = torch.empty(M, N, dtype=torch.float16, device=dev)
-        it = [0]
 
         def run_h():
-            it[0] += 1
-            torch.matmul(Ah, Wh[it[0] % ncopy], out=Dh)
+            for i in range(ncopy):
+                torch.matmul(Ah, Wh[i], out=Dh)
 
-        def run_q(s3):
-            it[0] += 1
-            qqq_b200.qqq_gemm(A, Bs[it[0] % ncopy], C, D, s1, s2, s3, ws, -1, -1, -1, 16)
-
-        n_it = 20 if M <= 1024 else 8
-        t_h = timed(run_h, n_it, 3, lambda: None) * 1e3
+        reps = 5 if M <= 1024 else 2
+        t_h = graph_time_us(run_h, ncopy, reps)
         fl = 2.0 * M * K * N
         for mode, s3 in (("per-channel", s3e), ("g128", s3g)):
-            t = timed(lambda: run_q(s3), n_it, 3, lambda: None) * 1e3  # us
+            def run_q():
+                for i in range(ncopy):
+                    qqq_b200.qqq_gemm(A, Bs[i], C, D, s1, s2, s3, ws, -1, -1, -1, 16)
+
+            t = graph_time_us(run_q, ncopy, reps)
             by = M * K + K * N / 2 + 2 * M * N + 4 * M + 4 * N + (2 * (K // 128) * N if mode == "g128" else 0)
             hbm_frac = by / (t * 1e-6) / 1e9 / peaks["hbm_gbs"]
             tc_frac = fl / (t * 1e-6) / 1e12 / int8_peak
             out.append(dict(M=M, K=K, N=N, mode=mode, us=round(t, 2), tflops=round(fl / t * 1e-6, 1),
-                            fp16_cublas_us=round(t_h, 2), speedup_vs_fp16=round(t_h / t, 3),
-                            bound="hbm" if hbm_frac > tc_frac else "tensor",
+                            gbps=round(by / t * 1e-3, 1), fp16_cublas_us=round(t_h, 2),
+                            speedup_vs_fp16=round(t_h / t, 3), bound="hbm" if hbm_frac > tc_frac else "tensor",
                             roofline_frac=round(max(hbm_frac, tc_frac), 3)))
     return out
 

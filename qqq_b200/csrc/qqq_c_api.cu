@@ -244,7 +244,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   }
   // several k-blocks per pipeline stage so that barrier round trips and the single-thread MMA issue loop are
   // amortised over >= 512 tensor-pipe cycles (an MMA of N tokens takes ~N/2 cycles, 4 per k-block)
-  p.ksub = p.n_tok <= 32 ? 4 : (p.n_tok <= 128 ? 2 : 1);
+  p.ksub = p.n_tok <= 64 ? 4 : (p.n_tok <= 128 ? 2 : 1);
   if (env_ksub == 1 || env_ksub == 2 || env_ksub == 4) p.ksub = env_ksub;
   while (p.ksub > 1 && p.k_blocks < p.ksub) p.ksub >>= 1;
   p.k_units = (p.k_blocks + p.ksub - 1) / p.ksub;

@@ -48,6 +48,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// wait for two barriers, polling both so that their latencies overlap
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  bool a = mbar_try_wait(bar_a, par_a);
+  bool b = mbar_try_wait(bar_b, par_b);
+  while (!(a && b)) {
+    if (!a) a = mbar_try_wait(bar_a, par_a);
+    if (!b) b = mbar_try_wait(bar_b, par_b);
+  }
+}
+
 // ---- fences ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

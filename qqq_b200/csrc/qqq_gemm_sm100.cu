@@ -242,8 +242,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(bar_fullt + 8 * st.idx, st.phase);
-        mbar_wait(bar_afull + 8 * as.idx, as.phase);
+        mbar_wait2(bar_fullt + 8 * st.idx, st.phase, bar_afull + 8 * as.idx, as.phase);
         tc_fence_after();
         if (elect_one()) {
           QQQ_TR(5, u - u_begin + kb - kb0);
@@ -262,7 +261,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (kb == kb1 - 1) umma_commit(bar_dfull + 8 * dbuf);
           QQQ_TR(6, u - u_begin + kb - kb0);
         }
-        __syncwarp();
         st.advance();
         as.advance();
       }
@@ -361,7 +359,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const bool whole = (kb0 == 0 && kb1 == KU);
       const int first_cta = (tile * KU) / p.units_per_cta;
       const int parts = (tile * KU + KU - 1) / p.units_per_cta - first_cta + 1;
-      const int part = (int)blockIdx.x - first_cta;
       const float s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;
       __half* __restrict__ dcol = p.D + n;
       int* __restrict__ ccol = p.C + n;
@@ -400,26 +397,40 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       }
       const bool finish = whole || ticket == parts - 1;  // this CTA writes D for the tile
-      const int others = whole ? 0 : parts - 1;           // published partial tiles to add
+      const int others = (!whole && finish) ? parts - 1 : 0;  // published partial tiles the finisher adds
+
+      // partial sums published by the other contributors, prefetched one 16-row chunk ahead
+      int pre[16];
+      auto fetch_partials = [&](int mb, int* acc) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0;
+        if (!n_ok) return;
+        for (int pp = 0; pp < others; ++pp) {
+          const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + mb) * ldn;
+          if (mb + 16 <= rows) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] += __ldcg(src + (size_t)i * ldn);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (mb + i < rows) acc[i] += __ldcg(src + (size_t)i * ldn);
+          }
+        }
+      };
+      if (others > 0) fetch_partials(0, pre);
 
       for (int mb = 0; mb < rows; mb += 16) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_d + mb, r);
         tmem_wait_ld();
+        if (others > 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] += (uint32_t)pre[i];
+          if (mb + 16 < rows) fetch_partials(mb + 16, pre);
+        }
         if (!n_ok) continue;
         const bool full16 = mb + 16 <= rows;
         if (finish) {
-          for (int pp = 0; pp < others; ++pp) {
-            const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + mb) * ldn;
-            if (full16) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] += (uint32_t)__ldcg(src + (size_t)i * ldn);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (mb + i < rows) r[i] += (uint32_t)__ldcg(src + (size_t)i * ldn);
-            }
-          }
           __half* __restrict__ dp = dcol + (size_t)(m0 + mb) * ldn;
           const float4* s4 = reinterpret_cast<const float4*>(s1_sm + mb);
           if (full16) {  // branch-free fast path
