@@ -443,8 +443,13 @@ def main():
             line["cpu_baseline"], _ = cpu_baseline()
         print(json.dumps(line))
     if world > 1:
+        # CUDA graphs captured above hold references into the NCCL communicator; tearing the process group down
+        # underneath them can hang, so synchronise, flush and leave without running destructors.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
