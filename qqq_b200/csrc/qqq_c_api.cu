@@ -143,6 +143,13 @@ bool encode_2d_uncached(CUtensorMap* m, CUtensorMapDataType dt, const void* base
   return true;
 }
 
+// Programmatic dependent launch (on by default; QQQ_B200_PDL=0 disables it): the kernels call griddepcontrol.wait
+// before touching anything the preceding kernel in the stream may produce or still use.
+bool use_pdl() {
+  static const bool on = !(getenv("QQQ_B200_PDL") && atoi(getenv("QQQ_B200_PDL")) == 0);
+  return on;
+}
+
 // The reference's tile-shape validity rule (csrc/qqq_gemm.cu:867-916), applied for error parity only.
 bool reference_shape_ok(int n, int k, int thread_k, int thread_n) {
   static const int cfg[4][2] = {{128, 128}, {128, 64}, {64, 256}, {64, 128}};
@@ -304,7 +311,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
                  2 * kTileN, 8 * p.ksub, CU_TENSOR_MAP_SWIZZLE_NONE))
     return QQQ_ERR_CUDA;
 
-  cudaError_t e = launch_gemm(tmap_a, tmap_b, p, grouped, grid, dev, stream);
+  cudaError_t e = launch_gemm(tmap_a, tmap_b, p, grouped, grid, dev, stream, use_pdl());
   if (e != cudaSuccess) {
     set_err("kernel launch failed: %s", cudaGetErrorString(e));
     return QQQ_ERR_CUDA;
@@ -334,7 +341,7 @@ int qqq_act_quant_sm100a(const void* x, void* q, void* s1, int prob_m, int prob_
   }
   DeviceGuard guard(dev);
   if (!guard.ok) return QQQ_ERR_CUDA;
-  cudaError_t e = qqq::launch_act_quant(x, q, s1, prob_m, prob_k, reinterpret_cast<cudaStream_t>(stream_));
+  cudaError_t e = qqq::launch_act_quant(x, q, s1, prob_m, prob_k, reinterpret_cast<cudaStream_t>(stream_), use_pdl());
   if (e != cudaSuccess) {
     set_err("act_quant launch failed: %s", cudaGetErrorString(e));
     return QQQ_ERR_CUDA;

@@ -72,6 +72,10 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
+// Programmatic dependent launch: block until the grid this launch depends on has completed and its memory is
+// visible (no-op when the kernel was not launched with the programmatic-serialization attribute).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMEM -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -169,6 +173,6 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 // ---- host-side declarations (qqq_c_api.cu) ----------------------------------------------------------
-cudaError_t launch_act_quant(const void* x, void* q, void* s1, int M, int K, cudaStream_t stream);
+cudaError_t launch_act_quant(const void* x, void* q, void* s1, int M, int K, cudaStream_t stream, bool pdl);
 
 }  // namespace qqq

@@ -152,26 +152,30 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int ndbuf = p.n_tok <= 128 ? 2 : 1;
   QQQ_TR_INIT();
 
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    for (int i = 0; i < NSW; ++i) {
+  if (warp == 0) {
+    // barrier init spread over the lanes of warp 0
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
+    }
+    for (int i = lane; i < NSW; i += 32) {
       mbar_init(bar_fullw + 8 * i, 1);
       mbar_init(bar_emptyw + 8 * i, 4 * KSUB);
     }
-    for (int i = 0; i < NST; ++i) {
+    for (int i = lane; i < NST; i += 32) {
       mbar_init(bar_fullt + 8 * i, 1);
       mbar_init(bar_emptyt + 8 * i, 1);
     }
-    for (int i = 0; i < kMaxASlots; ++i) {
+    for (int i = lane; i < kMaxASlots; i += 32) {
       mbar_init(bar_afull + 8 * i, 4 * KSUB);
       mbar_init(bar_aempty + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_dfull + 8 * i, 1);
-      mbar_init(bar_dempty + 8 * i, 4);
+    if (lane < 2) {
+      mbar_init(bar_dfull + 8 * lane, 1);
+      mbar_init(bar_dempty + 8 * lane, 4);
     }
     mbar_fence_init();
+    __syncwarp();
   }
   if (warp == 1) tmem_alloc(smem_u32(&misc[0]), 512);
   tc_fence_before();
@@ -212,6 +216,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp == 2) {
     // ===================================== tokens producer ==================================
+    grid_dependency_wait();  // A8 is produced by the preceding kernel (activation quant); weights are not
     Ring st(NST);
     UnitIter it(u_begin, KU, p.m_tiles);
     for (int u = u_begin; u < u_end; ++u) {
@@ -345,6 +350,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int epi_tid = threadIdx.x - kEpiWarp0 * 32;
     const int m_pad = p.m_tiles * p.n_tok;  // rows of one split-K slot in C
     const size_t ldn = (size_t)p.N;
+    grid_dependency_wait();  // s1 comes from the preceding kernel; D / C / lock words may still be in use by it
     int seg = 0, staged_mt = -1;
     for (int u = u_begin; u < u_end; ++seg) {
       const int tile = u / KU, kb0 = u - tile * KU;
@@ -495,7 +501,7 @@ size_t gemm_smem_bytes(const GemmParams& p) {
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
-                        int grid, int dev, cudaStream_t stream) {
+                        int grid, int dev, cudaStream_t stream, bool pdl) {
   static bool attr_set[2][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
   auto kern = grouped ? qqq_gemm_kernel<true> : qqq_gemm_kernel<false>;
@@ -504,8 +510,17 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, co
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[grouped][dev] = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(tmap_a, tmap_b, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // overlap launch + prologue + weight prefetch
+  attr[0].val.programmaticStreamSerializationAllowed = 1;           // with the tail of the preceding kernel
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, p);
 }
 
 #ifdef QQQ_TRACE

@@ -44,6 +44,6 @@ struct GemmParams {
 
 size_t gemm_smem_bytes(const GemmParams& p);
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
-                        int grid, int dev, cudaStream_t stream);
+                        int grid, int dev, cudaStream_t stream, bool pdl);
 
 }  // namespace qqq
