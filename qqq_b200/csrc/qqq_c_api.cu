@@ -279,6 +279,8 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
     return QQQ_ERR_KERN_SHAPE;
   }
   p.stages_t = nst;
+  static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
+  p.unpack_groups = (env_grp == 2 || env_grp == 3) ? env_grp : (grouped ? 3 : 2);
   p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
 
   int grid = (sms > 0 && sms < di->sms) ? sms : di->sms;

@@ -146,6 +146,10 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   float* s1_sm = reinterpret_cast<float*>(misc + 4);                                            // [kMaxTok]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = p.unpack_groups;                 // 2 (per-channel) or 3 (per-group: the fp16 rescale is ALU-heavy)
+  const int epi_warp0 = kUnpackWarp0 + 4 * G;    // warps [epi_warp0, kWarps) drain the accumulators
+  const int n_epi = kWarps - epi_warp0;          // 8 or 4 epilogue warps
+  const int n_epi_thr = 32 * n_epi;
   const int KU = p.k_units;  // units per tile
   const int u_begin = min((long long)blockIdx.x * p.units_per_cta, (long long)p.total_units);
   const int u_end = min((long long)u_begin + p.units_per_cta, (long long)p.total_units);
@@ -172,10 +176,37 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     if (lane < 2) {
       mbar_init(bar_dfull + 8 * lane, 1);
-      mbar_init(bar_dempty + 8 * lane, 4);
+      mbar_init(bar_dempty + 8 * lane, n_epi);
     }
     mbar_fence_init();
     __syncwarp();
+  }
+  // Weight stages that fit the (still empty) ring are requested right away, before TMEM allocation and the
+  // CTA-wide barrier: the first DRAM round trip overlaps the rest of the prologue.
+  const int n_pre = min(NSW, u_end - u_begin);
+  auto issue_weights = [&](int stage, const UnitIter& it) {
+    const uint32_t full = bar_fullw + 8 * stage;
+    uint32_t sbytes = 0;
+    int nsub_valid = 0;
+    if (GROUPED) {
+      sbytes = (uint32_t)min(kTileN, p.N - it.nt * kTileN) * 2u;
+      nsub_valid = min(KSUB, p.k_blocks - it.kb * KSUB);
+    }
+    mbar_expect_tx(full, stage_w + sbytes * nsub_valid);
+    tma_load_2d(smem_u32(sW + stage * stage_w), &tmap_b, full, it.nt * (2 * kTileN), it.kb * KSUB * 8, p.hint_b);
+    if (GROUPED) {
+      for (int sub = 0; sub < nsub_valid; ++sub)
+        bulk_load_1d(smem_u32(sS + stage * stage_s + sub * kStageS),
+                     p.s3 + (size_t)(it.kb * KSUB + sub) * p.N + it.nt * kTileN, sbytes, full);
+    }
+  };
+  if (warp == 0) {
+    UnitIter it(u_begin, KU, p.m_tiles);
+    for (int i = 0; i < n_pre; ++i) {
+      if (elect_one()) issue_weights(i, it);
+      __syncwarp();
+      it.next(KU, p.m_tiles);
+    }
   }
   if (warp == 1) tmem_alloc(smem_u32(&misc[0]), 512);
   tc_fence_before();
@@ -190,24 +221,15 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // lane issues.  k sub-blocks past the end of K are zero-filled by TMA, so they add nothing.
     Ring st(NSW);
     UnitIter it(u_begin, KU, p.m_tiles);
-    for (int u = u_begin; u < u_end; ++u) {
+    for (int i = 0; i < n_pre; ++i) {  // already issued in the prologue
+      st.advance();
+      it.next(KU, p.m_tiles);
+    }
+    for (int u = u_begin + n_pre; u < u_end; ++u) {
       mbar_wait(bar_emptyw + 8 * st.idx, st.phase ^ 1);
       if (elect_one()) {
         QQQ_TR(0, u - u_begin);
-        const uint32_t full = bar_fullw + 8 * st.idx;
-        uint32_t sbytes = 0;
-        int nsub_valid = 0;
-        if (GROUPED) {
-          sbytes = (uint32_t)min(kTileN, p.N - it.nt * kTileN) * 2u;
-          nsub_valid = min(KSUB, p.k_blocks - it.kb * KSUB);
-        }
-        mbar_expect_tx(full, stage_w + sbytes * nsub_valid);
-        tma_load_2d(smem_u32(sW + st.idx * stage_w), &tmap_b, full, it.nt * (2 * kTileN), it.kb * KSUB * 8, p.hint_b);
-        if (GROUPED) {
-          for (int sub = 0; sub < nsub_valid; ++sub)
-            bulk_load_1d(smem_u32(sS + st.idx * stage_s + sub * kStageS),
-                         p.s3 + (size_t)(it.kb * KSUB + sub) * p.N + it.nt * kTileN, sbytes, full);
-        }
+        issue_weights(st.idx, it);
         QQQ_TR(1, u - u_begin);
       }
       __syncwarp();
@@ -271,9 +293,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       u += kb1 - kb0;
     }
-  } else if (warp >= kUnpackWarp0 && warp < kEpiWarp0) {
+  } else if (warp >= kUnpackWarp0 && warp < epi_warp0) {
     // ===================================== unpack warps =====================================
-    // Three groups of 4 warps take k sub-blocks round-robin; inside a group warp <-> TMEM lane quadrant
+    // G groups of 4 warps take k sub-blocks round-robin; inside a group warp <-> TMEM lane quadrant
     // q = warp % 4: channels [32q, 32q+32) of the tile = 64-channel block nb = q/2, 16-wide n-tiles j = 2(q%2)+{0,1}.
     const int grp = (warp - kUnpackWarp0) >> 2;
     const int q = warp & 3, nb = q >> 1, jp = q & 1;
@@ -339,15 +361,17 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           if (q == 0 && lane == 0) QQQ_TR(4, itn);
         }
-        turn = (turn == kUnpackGroups - 1) ? 0 : turn + 1;
+        turn = (turn == G - 1) ? 0 : turn + 1;
       }
       st.advance();
       as.advance();
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp >= epi_warp0) {
     // ===================================== epilogue warps ===================================
     const int q = warp & 3;
-    const int epi_tid = threadIdx.x - kEpiWarp0 * 32;
+    const int epi_tid = threadIdx.x - epi_warp0 * 32;
+    const int eh = (warp - epi_warp0) >> 2;  // which of the n_epi/4 warps of this quadrant: takes every (n_epi/4)-th chunk
+    const int mstep = 16 * (n_epi >> 2);
     const int m_pad = p.m_tiles * p.n_tok;  // rows of one split-K slot in C
     const size_t ldn = (size_t)p.N;
     grid_dependency_wait();  // s1 comes from the preceding kernel; D / C / lock words may still be in use by it
@@ -371,9 +395,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
       // per-token scales of this token tile -> smem (once per tile change), so the store loop has no global loads
       if (mt != staged_mt) {
-        named_bar_sync(1, 128);  // previous users of s1_sm are done
-        for (int i = epi_tid; i < p.n_tok; i += 128) s1_sm[i] = (m0 + i < p.M) ? __ldg(p.s1 + m0 + i) : 0.f;
-        named_bar_sync(1, 128);
+        named_bar_sync(1, n_epi_thr);  // previous users of s1_sm are done
+        for (int i = epi_tid; i < p.n_tok; i += n_epi_thr) s1_sm[i] = (m0 + i < p.M) ? __ldg(p.s1 + m0 + i) : 0.f;
+        named_bar_sync(1, n_epi_thr);
         staged_mt = mt;
       }
 
@@ -389,16 +413,16 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int ticket = 0;
       int* lock = p.locks + nt + p.n_tiles * mt;
       if (!whole) {
-        named_bar_sync(1, 128);
+        named_bar_sync(1, n_epi_thr);
         if (epi_tid == 0) misc[1] = (uint32_t)atomicAdd(lock, 1) & 0xFFFFu;
-        named_bar_sync(1, 128);
+        named_bar_sync(1, n_epi_thr);
         ticket = (int)misc[1];
         if (ticket == parts - 1) {
           if (epi_tid == 0) {
             while ((ld_acquire_gpu(lock) >> 16) != parts - 1) {
             }
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(1, n_epi_thr);
           __threadfence();  // order this thread's reads of the published partials after the acquire above
         }
       }
@@ -423,16 +447,16 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         }
       };
-      if (others > 0) fetch_partials(0, pre);
+      if (others > 0 && 16 * eh < rows) fetch_partials(16 * eh, pre);
 
-      for (int mb = 0; mb < rows; mb += 16) {
+      for (int mb = 16 * eh; mb < rows; mb += mstep) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(tmem_d + mb, r);
         tmem_wait_ld();
         if (others > 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] += (uint32_t)pre[i];
-          if (mb + 16 < rows) fetch_partials(mb + 16, pre);
+          if (mb + mstep < rows) fetch_partials(mb + mstep, pre);
         }
         if (!n_ok) continue;
         const bool full16 = mb + 16 <= rows;
@@ -474,11 +498,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
       if (!whole) {
         if (finish) {
-          named_bar_sync(1, 128);  // every warp has read the published partials
+          named_bar_sync(1, n_epi_thr);  // every warp has read the published partials
           if (epi_tid == 0) *lock = 0;
         } else {
           __threadfence();  // partial tile visible device-wide before it is announced
-          named_bar_sync(1, 128);
+          named_bar_sync(1, n_epi_thr);
           if (epi_tid == 0) atomicAdd(lock, 0x10000);
         }
       }
