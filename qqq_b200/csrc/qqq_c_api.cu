@@ -280,10 +280,10 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   }
   p.stages_t = nst;
   static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
-  // decode-size tiles: the unpack rate bounds the weight stream (more unpack warps); large tiles: the accumulator
-  // drain is the exposed part (more epilogue warps).  The per-group rescale needs one more group than per-channel.
-  const int g_auto = (p.n_tok <= 64 ? 3 : 2) + (grouped ? 1 : 0);
-  p.unpack_groups = (env_grp >= 2 && env_grp <= 4) ? env_grp : g_auto;
+  // decode-size tiles and the ALU-heavy per-group rescale: 3 unpack groups + 4 epilogue warps; large per-channel
+  // tiles: the accumulator drain is the exposed part, so 2 unpack groups + 8 epilogue warps.
+  const int g_auto = (grouped || p.n_tok <= 64) ? 3 : 2;
+  p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
   p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
 
   int grid = (sms > 0 && sms < di->sms) ? sms : di->sms;

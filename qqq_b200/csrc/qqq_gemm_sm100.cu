@@ -11,7 +11,7 @@
 //   warp 0  weights producer : TMA of the packed int4 tile [8*KSUB rows x 1 KB] straight from the reference
 //                              layout (B int32 [K/16,2N]) + the group-scale rows (per-group only)  -> ring W
 //   warp 2  tokens producer  : TMA of the int8 token tile [n_tok x 128 B] (128B swizzle)           -> ring T
-//   8-16 unpack warps (2-4 groups of 4, one warp per TMEM lane quadrant): LDS.64 packed words -> int8 in registers
+//   8-12 unpack warps (2-3 groups of 4, one warp per TMEM lane quadrant): LDS.64 packed words -> int8 in registers
 //                              (per-channel: 2 logic ops per word; per-group: the reference's exact fp16-FMA
 //                              rounding, csrc/qqq_gemm.cu:167-210) -> tcgen05.st.16x128b into a TMEM ring.
 //                              The reference word layout (one word = 4 k x {n, n+8}) IS the 16x128b store
@@ -19,7 +19,7 @@
 //                              shuffle, shared-memory round trip or load-time repack.
 //   warp 1  MMA issuer       : tcgen05.mma.cta_group::1.kind::i8, A from TMEM, B (tokens) from a smem descriptor,
 //                              int32 accumulators in TMEM (double-buffered when n_tok <= 128)
-//   4-12 epilogue warps      : tcgen05.ld -> fp32 * s2[n] * s1[m] (reference order, :695-700) -> fp16 -> D
+//   4-8 epilogue warps       : tcgen05.ld -> fp32 * s2[n] * s1[m] (reference order, :695-700) -> fp16 -> D
 //
 // The two smem rings are decoupled: weight stages are released by the unpack warps as soon as they are in
 // registers, token stages by tcgen05.commit when the MMAs that read them retire; the TMEM ring lets the unpack
@@ -146,9 +146,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   float* s1_sm = reinterpret_cast<float*>(misc + 4);                                            // [kMaxTok]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int G = p.unpack_groups;                 // 2..4 groups of unpack warps (host policy in qqq_c_api.cu)
+  const int G = p.unpack_groups;                 // 2 or 3 groups of unpack warps (host policy in qqq_c_api.cu)
   const int epi_warp0 = kUnpackWarp0 + 4 * G;    // warps [epi_warp0, kWarps) drain the accumulators
-  const int n_epi = kWarps - epi_warp0;          // 12, 8 or 4 epilogue warps
+  const int n_epi = kWarps - epi_warp0;          // 8 or 4 epilogue warps
   const int n_epi_thr = 32 * n_epi;
   const int KU = p.k_units;  // units per tile
   const int u_begin = min((long long)blockIdx.x * p.units_per_cta, (long long)p.total_units);

@@ -19,9 +19,11 @@ constexpr int kMaxStages = 16;
 constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
 constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
 // warp roles: 0 weights TMA, 1 MMA (+TMEM alloc), 2 tokens TMA, 3 idle, then 4*G unpack warps (G groups x 4 TMEM
-// lane quadrants) and the remaining 20-4G warps as epilogue (G = 2: 12 epilogue warps, G = 3: 8, G = 4: 4)
+// lane quadrants) and the remaining 16-4G warps as epilogue (G = 2: 8 epilogue warps, G = 3: 4).  24 warps
+// (G up to 4) were measured and did not help: all warps of a TMEM quadrant share one SM sub-partition, so extra
+// groups add latency hiding but no ALU throughput (profiles/r01/sweep_groups_24warps.log).
 constexpr int kUnpackWarp0 = 4;
-constexpr int kWarps = 24;
+constexpr int kWarps = 20;
 constexpr int kThreads = 32 * kWarps;
 
 struct GemmParams {
@@ -37,7 +39,7 @@ struct GemmParams {
   int ksub;          // 128-deep k sub-blocks per pipeline stage (1, 2 or 4): amortises barrier traffic at small n_tok
   int k_units;       // ceil(k_blocks / ksub): pipeline stages ("units") per tile
   int stages_w, stages_t;  // depth of the weight / token smem rings
-  int unpack_groups;       // 2..4 groups of 4 unpack warps; the other 20-4G non-control warps are epilogue warps
+  int unpack_groups;       // 2 or 3 groups of 4 unpack warps; the other 16-4G non-control warps are epilogue warps
   int units_per_cta;  // stream-K: CTA b owns units [b*upc, (b+1)*upc); a unit = (tile, k-unit), tile = mt + m_tiles*nt
   int total_units;
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
