@@ -233,12 +233,30 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   p.M = M;
   p.N = N;
   p.K = K;
-  // token tiling: the whole batch in one UMMA-N tile up to 256 tokens, otherwise equal tiles of <= 256
-  p.m_tiles = (M + kMaxTok - 1) / kMaxTok;
-  const int per_tile = (M + p.m_tiles - 1) / p.m_tiles;
-  p.n_tok = (per_tile + 15) / 16 * 16;
+  // token tiling: the whole batch in one UMMA-N tile up to 256 tokens, otherwise equal tiles of <= 256 ...
   p.n_tiles = (N + kTileN - 1) / kTileN;
   p.k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int sm_count = (sms > 0 && sms < di->sms) ? sms : di->sms;
+  auto tile_tokens = [&](int cap, int* m_tiles) {
+    *m_tiles = (M + cap - 1) / cap;
+    const int per_tile = (M + *m_tiles - 1) / *m_tiles;
+    return (per_tile + 15) / 16 * 16;
+  };
+  p.n_tok = tile_tokens(kMaxTok, &p.m_tiles);
+  if (M > kMaxTok) {
+    // ... unless 128-token tiles fill the SMs so much better that they win despite their lower per-tile
+    // efficiency (measured ~0.85 of a 256-token tile): e.g. narrow tensor-parallel shards with fewer tiles than SMs.
+    // Whole-tile waves are compared; stream-K (below) only smooths the remainder.
+    int mt128 = 0;
+    const int nt128 = tile_tokens(128, &mt128);
+    const double waves256 = (double)((long long)p.m_tiles * p.n_tiles + sm_count - 1) / sm_count;
+    const double waves128 = (double)((long long)mt128 * p.n_tiles + sm_count - 1) / sm_count;
+    const double cost256 = (double)(long long)waves256 * p.n_tok, cost128 = (double)(long long)waves128 * nt128 / 0.85;
+    if (cost128 < 0.95 * cost256) {
+      p.n_tok = nt128;
+      p.m_tiles = mt128;
+    }
+  }
   // Tuning overrides for experiments (not part of the ABI): QQQ_B200_NTOK caps the token tile, QQQ_B200_KSUB /
   // QQQ_B200_NST force the stage depth in k and the token ring depth.
   static const int env_ntok = getenv("QQQ_B200_NTOK") ? atoi(getenv("QQQ_B200_NTOK")) : 0;
@@ -286,7 +304,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
   p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
 
-  int grid = (sms > 0 && sms < di->sms) ? sms : di->sms;
+  int grid = sm_count;
   if ((long long)grid > units) grid = (int)units;
   // Stream-K (a tile's k-range shared by several CTAs) needs one slot of C per contributor but the last: C has
   // 64*max_par rows, a slot is m_tiles*n_tok rows; and one lock word per tile.  Otherwise tiles are distributed whole.
