@@ -19,6 +19,7 @@ SYMBOLS = (
     "qqq_b200_version",
     "qqq_b200_last_error",
     "qqq_b200_launch_count",
+    "qqq_b200_plan",
 )
 
 _lib = None
@@ -53,6 +54,8 @@ def load() -> ctypes.CDLL:
     lib.qqq_b200_last_error.restype = ctypes.c_char_p
     lib.qqq_b200_launch_count.argtypes = []
     lib.qqq_b200_launch_count.restype = ctypes.c_longlong
+    lib.qqq_b200_plan.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.POINTER(ci)]
+    lib.qqq_b200_plan.restype = ci
     _lib = lib
     return lib
 

@@ -163,6 +163,123 @@ bool reference_shape_ok(int n, int k, int thread_k, int thread_n) {
   return false;
 }
 
+// Pure host-side planning (no CUDA calls): tiling, pipeline depths and the two-phase schedule for a problem on
+// `sm_count` SMs.  Exported as qqq_b200_plan() so the schedule can be checked exhaustively on a CPU-only machine.
+int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool has_scratch, qqq::GemmParams& p,
+              int* grid_out) {
+  using namespace qqq;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  // token tiling: the whole batch in one UMMA-N tile up to 256 tokens, otherwise equal tiles of <= 256 ...
+  p.n_tiles = (N + kTileN - 1) / kTileN;
+  p.k_blocks = (K + kBlockK - 1) / kBlockK;
+  auto tile_tokens = [&](int cap, int* m_tiles) {
+    *m_tiles = (M + cap - 1) / cap;
+    const int per_tile = (M + *m_tiles - 1) / *m_tiles;
+    return (per_tile + 15) / 16 * 16;
+  };
+  p.n_tok = tile_tokens(kMaxTok, &p.m_tiles);
+  if (M > kMaxTok) {
+    // ... unless 128-token tiles fill the SMs so much better that they win despite their lower per-tile
+    // efficiency (measured ~0.85 of a 256-token tile): e.g. narrow tensor-parallel shards with fewer tiles than SMs.
+    // Whole-tile waves are compared; stream-K (below) only smooths the remainder.
+    int mt128 = 0;
+    const int nt128 = tile_tokens(128, &mt128);
+    const double waves256 = (double)((long long)p.m_tiles * p.n_tiles + sm_count - 1) / sm_count;
+    const double waves128 = (double)((long long)mt128 * p.n_tiles + sm_count - 1) / sm_count;
+    const double cost256 = (double)(long long)waves256 * p.n_tok, cost128 = (double)(long long)waves128 * nt128 / 0.85;
+    if (cost128 < 0.95 * cost256) {
+      p.n_tok = nt128;
+      p.m_tiles = mt128;
+    }
+  }
+  // Tuning overrides for experiments (not part of the ABI): QQQ_B200_NTOK caps the token tile, QQQ_B200_KSUB /
+  // QQQ_B200_NST force the stage depth in k and the token ring depth.
+  static const int env_ntok = getenv("QQQ_B200_NTOK") ? atoi(getenv("QQQ_B200_NTOK")) : 0;
+  static const int env_ksub = getenv("QQQ_B200_KSUB") ? atoi(getenv("QQQ_B200_KSUB")) : 0;
+  static const int env_nst = getenv("QQQ_B200_NST") ? atoi(getenv("QQQ_B200_NST")) : 0;
+  if (env_ntok >= 16 && env_ntok <= kMaxTok && env_ntok % 16 == 0 && p.n_tok > env_ntok) {
+    p.m_tiles = (M + env_ntok - 1) / env_ntok;
+    const int pt = (M + p.m_tiles - 1) / p.m_tiles;
+    p.n_tok = (pt + 15) / 16 * 16;
+  }
+  // several k-blocks per pipeline stage so that barrier round trips and the single-thread MMA issue loop are
+  // amortised over >= 512 tensor-pipe cycles (an MMA of N tokens takes ~N/2 cycles, 4 per k-block)
+  p.ksub = p.n_tok <= 64 ? 4 : (p.n_tok <= 128 ? 2 : 1);
+  if (env_ksub == 1 || env_ksub == 2 || env_ksub == 4) p.ksub = env_ksub;
+  while (p.ksub > 1 && p.k_blocks < p.ksub) p.ksub >>= 1;
+  p.k_units = (p.k_blocks + p.ksub - 1) / p.ksub;
+  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  const long long units = tiles * p.k_units;
+  if (units >= (1ll << 31)) {
+    set_err("problem too large");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  // smem rings: tokens get enough stages to cover L2 latency at the MMA's consumption rate (~128 KB in flight,
+  // 3..6 stages), the weight ring takes the rest (it is drained by the unpack warps, far ahead of the MMA)
+  const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
+  const int budget = kMaxSmemBytes - 1024 - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
+  int nst = (131072 + stage_t - 1) / stage_t;
+  nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
+  if (env_nst >= 2 && env_nst <= kMaxStages) nst = env_nst;
+  int nsw = 0;
+  for (; nst >= 2; --nst) {
+    nsw = (budget - nst * stage_t) / stage_w;
+    if (nsw >= 3) break;
+  }
+  if (nst < 2 || nsw < 2) {
+    set_err("internal: no room for the smem rings (n_tok=%d ksub=%d)", p.n_tok, p.ksub);
+    return QQQ_ERR_KERN_SHAPE;
+  }
+  p.stages_t = nst;
+  static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
+  // decode-size tiles and the ALU-heavy per-group rescale: 3 unpack groups + 4 epilogue warps; large per-channel
+  // tiles: the accumulator drain is the exposed part, so 2 unpack groups + 8 epilogue warps.
+  const int g_auto = (grouped || p.n_tok <= 64) ? 3 : 2;
+  p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
+  p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
+
+  int grid = sm_count;
+  if ((long long)grid > units) grid = (int)units;
+  // Schedule.  Whole tiles go round the CTAs in waves; the remainder tiles that would leave SMs idle in a last
+  // partial wave are instead cut along K over all CTAs (stream-K) when the caller's scratch allows it: a split tile
+  // needs one slot of C (m_tiles*n_tok rows of the 64*max_par) per contributor but the last, and one lock word.
+  const long long whole_per_cta = tiles / grid;
+  const long long rem = tiles - whole_per_cta * grid;
+  long long a_tiles = 0, a_upc = 1;
+  if (rem > 0 && has_scratch && tiles <= (long long)(N / 128) * max_par && (double)rem / grid < 0.92) {
+    const long long slot_rows = (long long)p.m_tiles * p.n_tok, c_rows = 64ll * max_par;
+    auto parts_max = [&](long long upc) { return (upc % p.k_units == 0) ? 1ll : (p.k_units - 1) / upc + 2; };
+    // (1) cut only the remainder tiles, over all CTAs, ahead of the whole tiles (fix-up hidden behind the rest)
+    const long long upc_rem = (rem * p.k_units + grid - 1) / grid;
+    // (2) fallback when C is too small for that many contributors per tile: one contiguous stream-K range per CTA
+    //     over ALL tiles (at most 2-3 contributors per tile, but the fix-up of a CTA's last tile is exposed)
+    const long long upc_all = (units + grid - 1) / grid;
+    if ((parts_max(upc_rem) - 1) * slot_rows <= c_rows) {
+      a_tiles = rem;
+      a_upc = upc_rem;
+    } else if ((parts_max(upc_all) - 1) * slot_rows <= c_rows) {
+      a_tiles = tiles;
+      a_upc = upc_all;
+    }
+  }
+  p.a_tiles = (int)a_tiles;
+  p.a_units = (int)(a_tiles * p.k_units);
+  p.a_upc = (int)a_upc;
+  p.b_tiles = (int)(tiles - a_tiles);
+  p.b_tpc = (int)((p.b_tiles + grid - 1) / grid);
+  if (p.b_tiles > 0) {
+    const int used = (p.b_tiles + p.b_tpc - 1) / p.b_tpc;  // CTAs that get whole tiles
+    const int used_a = p.a_units > 0 ? (int)((p.a_units + a_upc - 1) / a_upc) : 0;
+    grid = used > used_a ? used : used_a;
+  } else {
+    grid = (int)((p.a_units + a_upc - 1) / a_upc);
+  }
+  *grid_out = grid;
+  return QQQ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -170,6 +287,20 @@ extern "C" {
 int qqq_b200_version(void) { return 100; }
 const char* qqq_b200_last_error(void) { return g_err; }
 long long qqq_b200_launch_count(void) { return g_launches.load(); }
+
+int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_count, int max_par, int* out /* [16] */) {
+  qqq::GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int grid = 0;
+  if (prob_m <= 0 || prob_n <= 0 || prob_k <= 0 || sm_count <= 0 || out == nullptr) return QQQ_ERR_PROB_SHAPE;
+  const int rc = plan_gemm(prob_m, prob_n, prob_k, groupsize == 128, sm_count, max_par, true, p, &grid);
+  if (rc != QQQ_OK) return rc;
+  const int v[16] = {grid,      p.n_tok,   p.m_tiles, p.n_tiles,  p.k_blocks, p.ksub,    p.k_units,      p.a_tiles,
+                     p.a_units, p.a_upc,   p.b_tiles, p.b_tpc,    p.stages_w, p.stages_t, p.unpack_groups,
+                     (int)qqq::gemm_smem_bytes(p)};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return QQQ_OK;
+}
 
 int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
                     int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
@@ -233,95 +364,12 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   p.M = M;
   p.N = N;
   p.K = K;
-  // token tiling: the whole batch in one UMMA-N tile up to 256 tokens, otherwise equal tiles of <= 256 ...
-  p.n_tiles = (N + kTileN - 1) / kTileN;
-  p.k_blocks = (K + kBlockK - 1) / kBlockK;
   const int sm_count = (sms > 0 && sms < di->sms) ? sms : di->sms;
-  auto tile_tokens = [&](int cap, int* m_tiles) {
-    *m_tiles = (M + cap - 1) / cap;
-    const int per_tile = (M + *m_tiles - 1) / *m_tiles;
-    return (per_tile + 15) / 16 * 16;
-  };
-  p.n_tok = tile_tokens(kMaxTok, &p.m_tiles);
-  if (M > kMaxTok) {
-    // ... unless 128-token tiles fill the SMs so much better that they win despite their lower per-tile
-    // efficiency (measured ~0.85 of a 256-token tile): e.g. narrow tensor-parallel shards with fewer tiles than SMs.
-    // Whole-tile waves are compared; stream-K (below) only smooths the remainder.
-    int mt128 = 0;
-    const int nt128 = tile_tokens(128, &mt128);
-    const double waves256 = (double)((long long)p.m_tiles * p.n_tiles + sm_count - 1) / sm_count;
-    const double waves128 = (double)((long long)mt128 * p.n_tiles + sm_count - 1) / sm_count;
-    const double cost256 = (double)(long long)waves256 * p.n_tok, cost128 = (double)(long long)waves128 * nt128 / 0.85;
-    if (cost128 < 0.95 * cost256) {
-      p.n_tok = nt128;
-      p.m_tiles = mt128;
-    }
+  int grid = 0;
+  {
+    const int rc = plan_gemm(M, N, K, grouped, sm_count, max_par, C != nullptr && workspace != nullptr, p, &grid);
+    if (rc != QQQ_OK) return rc;
   }
-  // Tuning overrides for experiments (not part of the ABI): QQQ_B200_NTOK caps the token tile, QQQ_B200_KSUB /
-  // QQQ_B200_NST force the stage depth in k and the token ring depth.
-  static const int env_ntok = getenv("QQQ_B200_NTOK") ? atoi(getenv("QQQ_B200_NTOK")) : 0;
-  static const int env_ksub = getenv("QQQ_B200_KSUB") ? atoi(getenv("QQQ_B200_KSUB")) : 0;
-  static const int env_nst = getenv("QQQ_B200_NST") ? atoi(getenv("QQQ_B200_NST")) : 0;
-  if (env_ntok >= 16 && env_ntok <= kMaxTok && env_ntok % 16 == 0 && p.n_tok > env_ntok) {
-    p.m_tiles = (M + env_ntok - 1) / env_ntok;
-    const int pt = (M + p.m_tiles - 1) / p.m_tiles;
-    p.n_tok = (pt + 15) / 16 * 16;
-  }
-  // several k-blocks per pipeline stage so that barrier round trips and the single-thread MMA issue loop are
-  // amortised over >= 512 tensor-pipe cycles (an MMA of N tokens takes ~N/2 cycles, 4 per k-block)
-  p.ksub = p.n_tok <= 64 ? 4 : (p.n_tok <= 128 ? 2 : 1);
-  if (env_ksub == 1 || env_ksub == 2 || env_ksub == 4) p.ksub = env_ksub;
-  while (p.ksub > 1 && p.k_blocks < p.ksub) p.ksub >>= 1;
-  p.k_units = (p.k_blocks + p.ksub - 1) / p.ksub;
-  const long long tiles = (long long)p.m_tiles * p.n_tiles;
-  const long long units = tiles * p.k_units;
-  if (units >= (1ll << 31)) {
-    set_err("problem too large");
-    return QQQ_ERR_PROB_SHAPE;
-  }
-  p.total_units = (int)units;
-  // smem rings: tokens get enough stages to cover L2 latency at the MMA's consumption rate (~128 KB in flight,
-  // 3..6 stages), the weight ring takes the rest (it is drained by the unpack warps, far ahead of the MMA)
-  const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
-  const int budget = kMaxSmemBytes - 1024 - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
-  int nst = (131072 + stage_t - 1) / stage_t;
-  nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
-  if (env_nst >= 2 && env_nst <= kMaxStages) nst = env_nst;
-  int nsw = 0;
-  for (; nst >= 2; --nst) {
-    nsw = (budget - nst * stage_t) / stage_w;
-    if (nsw >= 3) break;
-  }
-  if (nst < 2 || nsw < 2) {
-    set_err("internal: no room for the smem rings (n_tok=%d ksub=%d)", p.n_tok, p.ksub);
-    return QQQ_ERR_KERN_SHAPE;
-  }
-  p.stages_t = nst;
-  static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
-  // decode-size tiles and the ALU-heavy per-group rescale: 3 unpack groups + 4 epilogue warps; large per-channel
-  // tiles: the accumulator drain is the exposed part, so 2 unpack groups + 8 epilogue warps.
-  const int g_auto = (grouped || p.n_tok <= 64) ? 3 : 2;
-  p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
-  p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
-
-  int grid = sm_count;
-  if ((long long)grid > units) grid = (int)units;
-  // Stream-K (a tile's k-range shared by several CTAs) needs one slot of C per contributor but the last: C has
-  // 64*max_par rows, a slot is m_tiles*n_tok rows; and one lock word per tile.  Otherwise tiles are distributed whole.
-  const long long upc_split = (units + grid - 1) / grid;
-  const long long tiles_per_cta = (tiles + grid - 1) / grid;
-  const int parts_max = (upc_split % p.k_units == 0) ? 1 : (int)((p.k_units - 1) / upc_split) + 2;
-  const bool can_split = C != nullptr && workspace != nullptr &&
-                         (long long)(parts_max - 1) * p.m_tiles * p.n_tok <= 64ll * max_par &&
-                         tiles <= (long long)(N / 128) * max_par;
-  // splitting pays when whole-tile distribution would leave SMs idle for a noticeable part of the run
-  const double eff_whole = (double)tiles / (double)(tiles_per_cta * grid);
-  if (can_split && eff_whole < 0.92) {
-    p.units_per_cta = (int)upc_split;
-  } else {
-    p.units_per_cta = (int)(tiles_per_cta * p.k_units);
-  }
-  grid = (int)((units + p.units_per_cta - 1) / p.units_per_cta);
   // weights are streamed once when a single token tile covers M; tokens are re-read by every CTA
   p.hint_b = p.m_tiles == 1 ? kEvictFirst : kEvictNormal;
   p.hint_a = kEvictLast;

@@ -64,22 +64,31 @@ struct Ring {
   }
 };
 
-// walks units u = (tile, k-unit) with tile = mt + m_tiles * nt, without divisions in the loop
-struct UnitIter {
-  int kb, mt, nt;
-  __device__ UnitIter(int u, int KU, int m_tiles) {
-    const int tile = u / KU;
-    kb = u - tile * KU;
-    nt = tile / m_tiles;
-    mt = tile - nt * m_tiles;
+// Two-phase static schedule.  Phase A: the `a_tiles` remainder tiles that do not fill a whole wave are cut along K
+// into `a_upc`-unit slices, one slice per CTA (stream-K; a slice may straddle a tile boundary) — processed FIRST, so
+// their split-K fix-up overlaps the rest of the CTA's work.  Phase B: `b_tpc` whole tiles per CTA, processed last, so
+// the exposed tail of a CTA is a plain epilogue.  Every warp role walks the same segment list.
+struct Sched {
+  int KU, a_begin, a_end, n_a, b_first, n_b;
+  __device__ Sched(const GemmParams& p, int cta) {
+    KU = p.k_units;
+    a_begin = min(cta * p.a_upc, p.a_units);
+    a_end = min(a_begin + p.a_upc, p.a_units);
+    n_a = a_end > a_begin ? (a_end - 1) / KU - a_begin / KU + 1 : 0;
+    b_first = p.a_tiles + cta * p.b_tpc;
+    n_b = max(0, min(p.b_tpc, p.a_tiles + p.b_tiles - b_first));
   }
-  __device__ __forceinline__ void next(int KU, int m_tiles) {
-    if (++kb == KU) {
-      kb = 0;
-      if (++mt == m_tiles) {
-        mt = 0;
-        ++nt;
-      }
+  __device__ __forceinline__ int num_segments() const { return n_a + n_b; }
+  __device__ __forceinline__ int num_units() const { return (a_end - a_begin) + n_b * KU; }
+  __device__ __forceinline__ void segment(int i, int& tile, int& kb0, int& kb1) const {
+    if (i < n_a) {
+      tile = a_begin / KU + i;
+      kb0 = i == 0 ? a_begin - tile * KU : 0;
+      kb1 = min(KU, a_end - tile * KU);
+    } else {
+      tile = b_first + (i - n_a);
+      kb0 = 0;
+      kb1 = KU;
     }
   }
 };
@@ -151,8 +160,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int n_epi = kWarps - epi_warp0;          // 8 or 4 epilogue warps
   const int n_epi_thr = 32 * n_epi;
   const int KU = p.k_units;  // units per tile
-  const int u_begin = min((long long)blockIdx.x * p.units_per_cta, (long long)p.total_units);
-  const int u_end = min((long long)u_begin + p.units_per_cta, (long long)p.total_units);
+  const Sched sched(p, (int)blockIdx.x);
+  const int n_seg = sched.num_segments();
   const int ndbuf = p.n_tok <= 128 ? 2 : 1;
   QQQ_TR_INIT();
 
@@ -183,29 +192,40 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
   // Weight stages that fit the (still empty) ring are requested right away, before TMEM allocation and the
   // CTA-wide barrier: the first DRAM round trip overlaps the rest of the prologue.
-  const int n_pre = min(NSW, u_end - u_begin);
-  auto issue_weights = [&](int stage, const UnitIter& it) {
+  auto issue_weights = [&](int stage, int nt, int kb) {
     const uint32_t full = bar_fullw + 8 * stage;
     uint32_t sbytes = 0;
     int nsub_valid = 0;
     if (GROUPED) {
-      sbytes = (uint32_t)min(kTileN, p.N - it.nt * kTileN) * 2u;
-      nsub_valid = min(KSUB, p.k_blocks - it.kb * KSUB);
+      sbytes = (uint32_t)min(kTileN, p.N - nt * kTileN) * 2u;
+      nsub_valid = min(KSUB, p.k_blocks - kb * KSUB);
     }
     mbar_expect_tx(full, stage_w + sbytes * nsub_valid);
-    tma_load_2d(smem_u32(sW + stage * stage_w), &tmap_b, full, it.nt * (2 * kTileN), it.kb * KSUB * 8, p.hint_b);
+    tma_load_2d(smem_u32(sW + stage * stage_w), &tmap_b, full, nt * (2 * kTileN), kb * KSUB * 8, p.hint_b);
     if (GROUPED) {
       for (int sub = 0; sub < nsub_valid; ++sub)
         bulk_load_1d(smem_u32(sS + stage * stage_s + sub * kStageS),
-                     p.s3 + (size_t)(it.kb * KSUB + sub) * p.N + it.nt * kTileN, sbytes, full);
+                     p.s3 + (size_t)(kb * KSUB + sub) * p.N + nt * kTileN, sbytes, full);
     }
   };
+  // Weight producer state (warp 0): the first ring of stages is requested before TMEM allocation and the CTA-wide
+  // barrier, the rest in the role loop below.
+  int w_seg = 0, w_tile = 0, w_kb = 0, w_kb1 = 0, w_count = 0;
+  Ring w_st(NSW);
+  auto w_next = [&]() {  // advance to the next unit; false when the CTA's work is exhausted
+    while (w_kb >= w_kb1) {
+      if (w_seg >= n_seg) return false;
+      sched.segment(w_seg++, w_tile, w_kb, w_kb1);
+    }
+    return true;
+  };
   if (warp == 0) {
-    UnitIter it(u_begin, KU, p.m_tiles);
-    for (int i = 0; i < n_pre; ++i) {
-      if (elect_one()) issue_weights(i, it);
+    while (w_count < NSW && w_next()) {
+      if (elect_one()) issue_weights(w_st.idx, w_tile / p.m_tiles, w_kb);
       __syncwarp();
-      it.next(KU, p.m_tiles);
+      w_st.advance();
+      ++w_kb;
+      ++w_count;
     }
   }
   if (warp == 1) tmem_alloc(smem_u32(&misc[0]), 512);
@@ -219,60 +239,58 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================================== weights producer =================================
     // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected
     // lane issues.  k sub-blocks past the end of K are zero-filled by TMA, so they add nothing.
-    Ring st(NSW);
-    UnitIter it(u_begin, KU, p.m_tiles);
-    for (int i = 0; i < n_pre; ++i) {  // already issued in the prologue
-      st.advance();
-      it.next(KU, p.m_tiles);
-    }
-    for (int u = u_begin + n_pre; u < u_end; ++u) {
-      mbar_wait(bar_emptyw + 8 * st.idx, st.phase ^ 1);
+    while (w_next()) {
+      mbar_wait(bar_emptyw + 8 * w_st.idx, w_st.phase ^ 1);
       if (elect_one()) {
-        QQQ_TR(0, u - u_begin);
-        issue_weights(st.idx, it);
-        QQQ_TR(1, u - u_begin);
+        QQQ_TR(0, w_count);
+        issue_weights(w_st.idx, w_tile / p.m_tiles, w_kb);
+        QQQ_TR(1, w_count);
       }
       __syncwarp();
-      st.advance();
-      it.next(KU, p.m_tiles);
+      w_st.advance();
+      ++w_kb;
+      ++w_count;
     }
   } else if (warp == 2) {
     // ===================================== tokens producer ==================================
     grid_dependency_wait();  // A8 is produced by the preceding kernel (activation quant); weights are not
     Ring st(NST);
-    UnitIter it(u_begin, KU, p.m_tiles);
-    for (int u = u_begin; u < u_end; ++u) {
-      mbar_wait(bar_emptyt + 8 * st.idx, st.phase ^ 1);
-      if (elect_one()) {
-        const uint32_t full = bar_fullt + 8 * st.idx;
-        mbar_expect_tx(full, stage_t);
-        for (int sub = 0; sub < KSUB; ++sub)
-          tma_load_2d(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, full, (it.kb * KSUB + sub) * kBlockK,
-                      it.mt * p.n_tok, p.hint_a);
+    for (int sg = 0; sg < n_seg; ++sg) {
+      int tile, kb0, kb1;
+      sched.segment(sg, tile, kb0, kb1);
+      const int mt = tile % p.m_tiles;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_emptyt + 8 * st.idx, st.phase ^ 1);
+        if (elect_one()) {
+          const uint32_t full = bar_fullt + 8 * st.idx;
+          mbar_expect_tx(full, stage_t);
+          for (int sub = 0; sub < KSUB; ++sub)
+            tma_load_2d(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, full, (kb * KSUB + sub) * kBlockK,
+                        mt * p.n_tok, p.hint_a);
+        }
+        __syncwarp();
+        st.advance();
       }
-      __syncwarp();
-      st.advance();
-      it.next(KU, p.m_tiles);
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     Ring st(NST), as(NA);
     const uint32_t idesc = make_idesc_i8(kTileN, p.n_tok);
     const uint64_t desc_tok0 = make_smem_desc(smem_u32(sT), 16, 1024, 2);  // + (byte offset >> 4) per stage / k-step
-    int seg = 0;
-    for (int u = u_begin; u < u_end; ++seg) {
-      const int tile = u / KU, kb0 = u - tile * KU;
-      const int kb1 = min(KU, kb0 + (u_end - u));
+    int ucount = 0;
+    for (int seg = 0; seg < n_seg; ++seg) {
+      int tile, kb0, kb1;
+      sched.segment(seg, tile, kb0, kb1);
       const int dbuf = seg % ndbuf;
       const uint32_t dph = (seg / ndbuf) & 1;
       mbar_wait(bar_dempty + 8 * dbuf, dph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb, ++ucount) {
         mbar_wait2(bar_fullt + 8 * st.idx, st.phase, bar_afull + 8 * as.idx, as.phase);
         tc_fence_after();
         if (elect_one()) {
-          QQQ_TR(5, u - u_begin + kb - kb0);
+          QQQ_TR(5, ucount);
           uint64_t desc = desc_tok0 + (uint64_t)((st.idx * stage_t) >> 4);
           uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32 * KSUB;
           for (int sub = 0; sub < KSUB; ++sub) {
@@ -286,12 +304,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           umma_commit(bar_aempty + 8 * as.idx);
           umma_commit(bar_emptyt + 8 * st.idx);
           if (kb == kb1 - 1) umma_commit(bar_dfull + 8 * dbuf);
-          QQQ_TR(6, u - u_begin + kb - kb0);
+          QQQ_TR(6, ucount);
         }
         st.advance();
         as.advance();
       }
-      u += kb1 - kb0;
     }
   } else if (warp >= kUnpackWarp0 && warp < epi_warp0) {
     // ===================================== unpack warps =====================================
@@ -303,7 +320,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     Ring st(NSW), as(NA);
     int turn = 0;  // which group owns the next sub-block
     int itn = 0;
-    for (int u = u_begin; u < u_end; ++u) {
+    const int n_units = sched.num_units();
+    for (int u = 0; u < n_units; ++u) {
       bool stage_ready = false, slot_ready = false;
       for (int sub = 0; sub < KSUB; ++sub, ++itn) {
         if (turn == grp) {
@@ -375,10 +393,10 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int m_pad = p.m_tiles * p.n_tok;  // rows of one split-K slot in C
     const size_t ldn = (size_t)p.N;
     grid_dependency_wait();  // s1 comes from the preceding kernel; D / C / lock words may still be in use by it
-    int seg = 0, staged_mt = -1;
-    for (int u = u_begin; u < u_end; ++seg) {
-      const int tile = u / KU, kb0 = u - tile * KU;
-      const int kb1 = min(KU, kb0 + (u_end - u));
+    int staged_mt = -1;
+    for (int seg = 0; seg < n_seg; ++seg) {
+      int tile, kb0, kb1;
+      sched.segment(seg, tile, kb0, kb1);
       const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
       const int dbuf = seg % ndbuf;
       const uint32_t dph = (seg / ndbuf) & 1;
@@ -387,8 +405,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int m0 = mt * p.n_tok;
       const int rows = min(p.n_tok, p.M - m0);  // valid token rows of this tile
       const bool whole = (kb0 == 0 && kb1 == KU);
-      const int first_cta = (tile * KU) / p.units_per_cta;
-      const int parts = (tile * KU + KU - 1) / p.units_per_cta - first_cta + 1;
+      // contributors of a phase-A tile: the CTAs whose slice [b*a_upc, (b+1)*a_upc) meets the tile's units
+      const int parts = whole ? 1 : (tile * KU + KU - 1) / p.a_upc - (tile * KU) / p.a_upc + 1;
       const float s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;
       __half* __restrict__ dcol = p.D + n;
       int* __restrict__ ccol = p.C + n;
@@ -507,7 +525,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       }
       if (epi_tid == 0) QQQ_TR(11, seg);
-      u += kb1 - kb0;
     }
   }
 

@@ -40,8 +40,12 @@ struct GemmParams {
   int k_units;       // ceil(k_blocks / ksub): pipeline stages ("units") per tile
   int stages_w, stages_t;  // depth of the weight / token smem rings
   int unpack_groups;       // 2 or 3 groups of 4 unpack warps; the other 16-4G non-control warps are epilogue warps
-  int units_per_cta;  // stream-K: CTA b owns units [b*upc, (b+1)*upc); a unit = (tile, k-unit), tile = mt + m_tiles*nt
-  int total_units;
+  // two-phase schedule (see Sched in qqq_gemm_sm100.cu); a unit = (tile, k-unit), tile = mt + m_tiles*nt
+  int a_tiles;  // tiles [0, a_tiles) are cut along K: CTA b owns phase-A units [b*a_upc, (b+1)*a_upc) of a_units
+  int a_units;  // a_tiles * k_units
+  int a_upc;    // >= 1 (1 when a_units == 0)
+  int b_tiles;  // tiles [a_tiles, a_tiles + b_tiles) are processed whole: CTA b owns b_tpc consecutive ones
+  int b_tpc;
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
 };
 

@@ -1,0 +1,88 @@
+"""CPU test of the host-side schedule (qqq_b200_plan, pure C++ host code in qqq_c_api.cu): for many problem
+shapes and SM counts, replay the kernel's segment walk (Sched in qqq_gemm_sm100.cu) and check that every
+(tile, k-unit) is produced exactly once, that split tiles fit the caller's scratch (C rows, lock words) and that
+the launch fits the SM's shared memory."""
+import ctypes
+
+import pytest
+
+from qqq_b200 import _lib
+
+KEYS = ["grid", "n_tok", "m_tiles", "n_tiles", "k_blocks", "ksub", "k_units", "a_tiles", "a_units", "a_upc", "b_tiles",
+        "b_tpc", "stages_w", "stages_t", "unpack_groups", "smem_bytes"]
+
+
+def plan(M, N, K, gs=-1, sms=148, max_par=16):
+    out = (ctypes.c_int * 16)()
+    rc = _lib.load().qqq_b200_plan(M, N, K, gs, sms, max_par, out)
+    assert rc == 0
+    return dict(zip(KEYS, out))
+
+
+def segments(p, cta):
+    """Python mirror of `struct Sched`."""
+    KU = p["k_units"]
+    a_begin = min(cta * p["a_upc"], p["a_units"])
+    a_end = min(a_begin + p["a_upc"], p["a_units"])
+    segs = []
+    if a_end > a_begin:
+        for t in range(a_begin // KU, (a_end - 1) // KU + 1):
+            segs.append((t, max(a_begin - t * KU, 0), min(KU, a_end - t * KU)))
+    b_first = p["a_tiles"] + cta * p["b_tpc"]
+    n_b = max(0, min(p["b_tpc"], p["a_tiles"] + p["b_tiles"] - b_first))
+    segs += [(b_first + i, 0, KU) for i in range(n_b)]
+    return segs
+
+
+SHAPES = [(1, 4096, 4096), (1, 21760, 8192), (16, 21760, 8192), (16, 128, 8192), (33, 4096, 14336), (64, 21760, 8192),
+          (100, 384, 1152), (128, 21760, 8192), (200, 1024, 1024), (256, 21760, 8192), (300, 640, 768),
+          (1000, 384, 512), (1024, 4096, 4096), (1024, 11008, 4096), (1024, 4096, 11008), (1024, 21760, 8192),
+          (1024, 2048, 4096), (1024, 1408, 4096), (1100, 256, 256), (4096, 21760, 8192), (4096, 4096, 4096),
+          (5, 128, 64), (7, 320, 1024), (2048, 8192, 1024)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("sms", [1, 3, 37, 132, 148])
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
+    if gs == 128 and K % 128:
+        pytest.skip("per-group needs K % 128 == 0")
+    p = plan(M, N, K, gs, sms)
+    KU, tiles = p["k_units"], p["m_tiles"] * p["n_tiles"]
+    assert p["a_tiles"] + p["b_tiles"] == tiles and p["a_units"] == p["a_tiles"] * KU
+    assert 1 <= p["grid"] <= sms
+    assert p["n_tok"] % 16 == 0 and 16 <= p["n_tok"] <= 256 and p["m_tiles"] * p["n_tok"] >= M
+    assert p["ksub"] in (1, 2, 4) and KU == -(-p["k_blocks"] // p["ksub"])
+    assert p["smem_bytes"] <= 232448 and p["stages_w"] >= 2 and p["stages_t"] >= 2
+    assert p["unpack_groups"] in (2, 3)
+    seen = {}
+    contributors = {}
+    for cta in range(p["grid"]):
+        for (t, kb0, kb1) in segments(p, cta):
+            assert 0 <= t < tiles and 0 <= kb0 < kb1 <= KU
+            for kb in range(kb0, kb1):
+                assert (t, kb) not in seen, f"unit {(t, kb)} produced twice"
+                seen[(t, kb)] = cta
+            contributors.setdefault(t, []).append(cta)
+    assert len(seen) == tiles * KU, "some unit is never produced"
+    # CTAs beyond the grid must have no work
+    assert segments(p, p["grid"]) == []
+    # split tiles: the kernel's contributor count formula, scratch capacity and lock words
+    slot_rows = p["m_tiles"] * p["n_tok"]
+    for t, ctas in contributors.items():
+        if len(ctas) > 1:
+            assert t < p["a_tiles"]
+            parts = (t * KU + KU - 1) // p["a_upc"] - (t * KU) // p["a_upc"] + 1
+            assert parts == len(ctas)
+            assert (parts - 1) * slot_rows <= 64 * 16, "split tile needs more rows than C has"
+    if any(len(c) > 1 for c in contributors.values()):
+        assert tiles <= (N // 128) * 16, "not enough lock words in workspace"
+
+
+def test_decode_plan_hides_the_fixup():
+    """At decode the split remainder tiles are processed first and every CTA ends on a whole tile."""
+    p = plan(16, 21760, 8192)
+    assert p["a_tiles"] == 170 - 148 and p["b_tpc"] == 1 and p["grid"] == 148
+    for cta in range(p["grid"]):
+        segs = segments(p, cta)
+        assert segs[-1][1:] == (0, p["k_units"])
