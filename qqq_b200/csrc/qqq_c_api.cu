@@ -256,7 +256,9 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     // (2) fallback when C is too small for that many contributors per tile: one contiguous stream-K range per CTA
     //     over ALL tiles (at most 2-3 contributors per tile, but the fix-up of a CTA's last tile is exposed)
     const long long upc_all = (units + grid - 1) / grid;
-    if ((parts_max(upc_rem) - 1) * slot_rows <= c_rows) {
+    // (1) multiplies the contributors per tile (and with them the partial-tile traffic of the fix-up), so it is
+    // used for decode-size tiles only; measured: wins at n_tok <= 32, loses from 64 tokens up.
+    if (p.n_tok <= 32 && (parts_max(upc_rem) - 1) * slot_rows <= c_rows) {
       a_tiles = rem;
       a_upc = upc_rem;
     } else if ((parts_max(upc_all) - 1) * slot_rows <= c_rows) {
