@@ -216,11 +216,11 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     set_err("problem too large");
     return QQQ_ERR_PROB_SHAPE;
   }
-  // smem rings: tokens get enough stages to cover L2 latency at the MMA's consumption rate (~128 KB in flight,
+  // smem rings: tokens get enough stages to cover L2 latency at the MMA's consumption rate (~160 KB in flight,
   // 3..6 stages), the weight ring takes the rest (it is drained by the unpack warps, far ahead of the MMA)
   const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
   const int budget = kMaxSmemBytes - 1024 - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
-  int nst = (131072 + stage_t - 1) / stage_t;
+  int nst = (163840 + stage_t - 1) / stage_t;  // ~160 KB of tokens in flight: (L2 latency + 512) / stages <= 512 cycles
   nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
   if (env_nst >= 2 && env_nst <= kMaxStages) nst = env_nst;
   int nsw = 0;
