@@ -216,18 +216,30 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     set_err("problem too large");
     return QQQ_ERR_PROB_SHAPE;
   }
-  // smem rings: tokens get enough stages to cover L2 latency at the MMA's consumption rate (~160 KB in flight,
-  // 3..6 stages), the weight ring takes the rest (it is drained by the unpack warps, far ahead of the MMA)
+  // smem rings.  Depth = latency x consumption rate: when one token tile covers M the weights stream from DRAM
+  // (long latency, ~160 KB in flight); with several token tiles they mostly hit L2 (~64 KB).  The token ring
+  // (L2-resident data) takes the rest, at least 3 and at most 6 stages.
   const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
   const int budget = kMaxSmemBytes - 1024 - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
-  int nst = (163840 + stage_t - 1) / stage_t;  // ~160 KB of tokens in flight: (L2 latency + 512) / stages <= 512 cycles
-  nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
-  if (env_nst >= 2 && env_nst <= kMaxStages) nst = env_nst;
-  int nsw = 0;
-  for (; nst >= 2; --nst) {
+  const int target_w = p.m_tiles == 1 ? 163840 : 65536;
+  int nsw = (target_w + stage_w - 1) / stage_w;
+  nsw = nsw < 3 ? 3 : (nsw > kMaxStages ? kMaxStages : nsw);
+  int nst = 0;
+  if (p.m_tiles > 1) {  // tensor-bound regime: the token ring comes first (~160 KB, (L2 latency + 512) / stages <= 512)
+    nst = (163840 + stage_t - 1) / stage_t;
+    nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
     nsw = (budget - nst * stage_t) / stage_w;
-    if (nsw >= 3) break;
+    if (nsw > kMaxStages) nsw = kMaxStages;
   }
+  if (p.m_tiles == 1 || nsw < 4) {
+    if (nsw < 3) nsw = 3;
+    for (; nsw >= 2; --nsw) {
+      nst = (budget - nsw * stage_w) / stage_t;
+      if (nst >= 3) break;
+    }
+  }
+  if (nst > 6) nst = 6;
+  if (env_nst >= 2 && env_nst <= kMaxStages && nsw * stage_w + env_nst * stage_t <= budget) nst = env_nst;
   if (nst < 2 || nsw < 2) {
     set_err("internal: no room for the smem rings (n_tok=%d ksub=%d)", p.n_tok, p.ksub);
     return QQQ_ERR_KERN_SHAPE;
