@@ -136,7 +136,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int NSW = p.stages_w, NST = p.stages_t;
   const int KSUB = p.ksub;                  // 128-deep k sub-blocks per pipeline stage ("unit")
-  const int NA = kASlotCols / (32 * KSUB);  // TMEM weight ring slots; one slot = one unit = 32*KSUB columns
+  // TMEM columns: accumulator buffers first (two when they leave >= 128 columns for the weight ring, so the drain of
+  // one tile overlaps the MMAs of the next), then the ring of unpacked weight tiles (one slot = one unit = 32*KSUB columns)
+  const int ndbuf = p.n_tok <= 192 ? 2 : 1;
+  const int tmem_a0 = ndbuf * p.n_tok;
+  const int NA = min(kMaxASlots, (512 - tmem_a0) / (32 * KSUB));
   const int tok_bytes = p.n_tok * 128;      // one sub-block of tokens
   const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
   uint8_t* sT = smem;
@@ -162,7 +166,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int KU = p.k_units;  // units per tile
   const Sched sched(p, (int)blockIdx.x);
   const int n_seg = sched.num_segments();
-  const int ndbuf = p.n_tok <= 128 ? 2 : 1;
   QQQ_TR_INIT();
 
   if (warp == 0) {
@@ -292,7 +295,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (elect_one()) {
           QQQ_TR(5, ucount);
           uint64_t desc = desc_tok0 + (uint64_t)((st.idx * stage_t) >> 4);
-          uint32_t tmem_a = tmem_base + kTmemColsA0 + as.idx * 32 * KSUB;
+          uint32_t tmem_a = tmem_base + tmem_a0 + as.idx * 32 * KSUB;
           for (int sub = 0; sub < KSUB; ++sub) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
@@ -344,7 +347,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           if (q == 0 && lane == 0) QQQ_TR(3, itn);
           const uint32_t tmem_a =
-              tmem_base + kTmemColsA0 + as.idx * 32 * KSUB + sub * 32 + ((uint32_t)(32 * q) << 16);
+              tmem_base + tmem_a0 + as.idx * 32 * KSUB + sub * 32 + ((uint32_t)(32 * q) << 16);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t s_b0 = 0, s_b1 = 0;

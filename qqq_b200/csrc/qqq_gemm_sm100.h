@@ -12,8 +12,6 @@ constexpr int kTileN = 128;      // output channels per CTA tile  (UMMA M)
 constexpr int kBlockK = 128;     // reduction depth of one k sub-block (= the per-group quantisation group)
 constexpr int kStageB = 8192;    // packed int4 bytes per sub-block: 8 rows of B x 256 words
 constexpr int kStageS = 256;     // group-scale bytes per sub-block: 128 channels x fp16
-constexpr int kTmemColsA0 = 256; // TMEM: accumulators in columns [0,256), unpacked weight ring in [256,512)
-constexpr int kASlotCols = 256;
 constexpr int kMaxASlots = 8;    // ring slots of 32*ksub columns each
 constexpr int kMaxStages = 16;
 constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
