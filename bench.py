@@ -160,6 +160,7 @@ def build_model(dev, rank, world, gen):
 
 
 def forward_chain(layers, h, world):
+    """The reference's module structure: 7 separate linears per layer (q, k, v re-quantise the same input)."""
     import torch.distributed as dist
 
     for m in layers:
@@ -178,12 +179,42 @@ def forward_chain(layers, h, world):
     return h
 
 
-def gemm_only_chain(layers, qin):
-    """The 224 GEMM launches alone, on pre-quantised inputs (for the roofline figure of the dominant kernel)."""
+def merge_layers(layers):
+    """q/k/v and gate/up merged by column concatenation of the packed tensors (qqq_b200.merge_quant_linears):
+    bit-identical outputs, one activation quant + one GEMM per group of linears that share their input."""
     import qqq_b200
 
+    merged = []
     for m in layers:
-        for (name, _, _, _) in LAYER_LINEARS:
+        merged.append(dict(qkv=qqq_b200.merge_quant_linears([m["q"], m["k"], m["v"]]), o=m["o"],
+                           gate_up=qqq_b200.merge_quant_linears([m["gate"], m["up"]]), down=m["down"]))
+    return merged
+
+
+def forward_chain_merged(mlayers, h, world):
+    import torch.distributed as dist
+
+    for m in mlayers:
+        qkv = m["qkv"](h)
+        q = qkv[:, : m["qkv"].split_sizes[0]]  # column slice, consumed in place by the strided activation quant
+        o = m["o"](q)
+        if world > 1:
+            dist.all_reduce(o)
+        gu = m["gate_up"](o)
+        g = gu[:, : m["gate_up"].split_sizes[0]]
+        d = m["down"](g)
+        if world > 1:
+            dist.all_reduce(d)
+        h = d
+    return h
+
+
+def gemm_only_chain(mlayers, qin):
+    """The GEMM launches of a step alone, on pre-quantised inputs (for the roofline figure of the dominant kernel)."""
+    import qqq_b200
+
+    for m in mlayers:
+        for name in ("qkv", "o", "gate_up", "down"):
             ql = m[name]
             A8, s1, D = qin[(ql.infeatures, ql.outfeatures)]
             qqq_b200.qqq_gemm(A8, ql.B, ql.reduce_buffer, D, s1, ql.s_channel, ql.s_group, ql.workspace, -1, -1, -1, 16)
@@ -329,8 +360,9 @@ def main():
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
     M = MODEL["seq"] * MODEL["batch"]
-    cfg = dict(workload="llama-2-7b prefill seq=1024 batch=1: all 224 quantized linears (per-channel W4A8), "
-                        "per linear = per-token act-quant + W4A8 GEMM; random-init weights",
+    cfg = dict(workload="llama-2-7b prefill seq=1024 batch=1: all 224 quantized linears (per-channel W4A8); q/k/v and "
+                        "gate/up merged by concatenating their packed tensors (bit-identical outputs): per layer 4 x "
+                        "(per-token act-quant + W4A8 GEMM); random-init weights",
                global_batch=MODEL["batch"], seq_len=MODEL["seq"], parallelism=f"tp{world}" if world > 1 else "single",
                l2="inputs larger than L2: 3.2 GB of packed weights stream from HBM every step")
 
@@ -365,21 +397,19 @@ def main():
     out_host = torch.empty(M, MODEL["hidden"], dtype=torch.float16).pin_memory()
     x_dev = x_host.to(dev)
 
-    # --- device-resident throughput (value): the 448 launches of a step are replayed from one CUDA graph ---
+    # --- device-resident throughput (value): a step's launches are replayed from one CUDA graph ---
     from qqq_b200 import graph as qgraph
 
+    mlayers = merge_layers(layers)
     l0 = qqq_b200.launch_count()
-    forward_chain(layers, x_dev, world)
+    forward_chain_merged(mlayers, x_dev, world)
     launches_per_step = qqq_b200.launch_count() - l0
-    graphed = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
+    graphed = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
     with ClockSampler(local_rank) as cs:
         ms = timed(lambda: graphed(x_dev), args.steps, args.warmup, barrier)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = M / (ms * 1e-3)
-
+    # the same 224 linears called module by module like the reference model (7 GEMMs + 7 activation quants per layer)
+    graphed_sep = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
+    ms_sep = timed(lambda: graphed_sep(x_dev), args.steps, args.warmup, barrier)
     # --- end to end: pinned host input -> H2D -> 224 linears -> D2H of the result, every step ---
     def e2e_step():
         h = graphed(x_host)  # pinned host -> static device input (H2D), graph replay
@@ -388,7 +418,7 @@ def main():
     # the same step through the eager public API (no graph), for the record
     def eager_step():
         x_dev.copy_(x_host, non_blocking=True)
-        out_host.copy_(forward_chain(layers, x_dev, world), non_blocking=True)
+        out_host.copy_(forward_chain_merged(mlayers, x_dev, world), non_blocking=True)
 
     ms_eager = timed(eager_step, args.steps, args.warmup, barrier)
 
@@ -400,29 +430,29 @@ def main():
 
     # --- dominant kernel alone: the 224 GEMM launches on pre-quantised inputs ---
     qin = {}
-    for (name, _, _, _) in LAYER_LINEARS:
-        ql = layers[0][name]
+    for name in ("qkv", "o", "gate_up", "down"):
+        ql = mlayers[0][name]
         key = (ql.infeatures, ql.outfeatures)
         if key not in qin:
             A8 = torch.randint(-127, 128, (M, key[0]), dtype=torch.int8, device=dev)
             qin[key] = (A8, torch.full((M, 1), 0.03, device=dev), torch.empty(M, key[1], dtype=torch.float16, device=dev))
     def _gemm_chain(x):
-        gemm_only_chain(layers, qin)
+        gemm_only_chain(mlayers, qin)
         return x
 
     graphed_gemm = qgraph.capture(_gemm_chain, x_dev)
     ms_gemm = timed(lambda: graphed_gemm(x_dev), args.steps, args.warmup, barrier)
-    n_gemm = MODEL["layers"] * len(LAYER_LINEARS)
+    n_gemm = MODEL["layers"] * 4
     flops_rank = model_flops(M) / world
     int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
     achieved = flops_rank / (ms_gemm * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01", "ncu", "traffic.json")
     if world == 1 and os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full captures
-        traffic = json.load(open(tpath))["llama2_7b_prefill_m1024"]["avg_per_launch"]
+        traffic = json.load(open(tpath)).get("llama2_7b_prefill_m1024_merged", {}).get("avg_per_launch")
     roofline = dict(bound="tensor", kernel="qqq_gemm_kernel<per-channel> (tcgen05 kind::i8)", achieved=round(achieved, 1),
                     peak=round(int8_peak, 1), unit="TFLOP/s", frac=round(achieved / int8_peak, 4), traffic=traffic,
-                    traffic_note="dram__bytes_read+write per launch, mean over the 7 linears of a layer (ncu, "
+                    traffic_note="dram__bytes_read+write per launch, mean over the 4 GEMMs of a layer (ncu, "
                                  "profiles/r01/ncu/traffic.json); below the algorithmic bytes because A8 and D stay in L2",
                     peak_source=f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['source']}); int8 dense = 2x bf16 "
                                 "on sm_100a; UTCIMMA-only microbenchmark on this pool measured 4428 TOP/s burst "
@@ -442,6 +472,9 @@ def main():
                                  f"{ms_eager:.3f} ms/step"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     launch_mode="cuda-graph replay of the per-step launches",
+                    unmerged=dict(ms_per_step=round(ms_sep, 4), value=round(M / (ms_sep * 1e-3), 1),
+                                  note="same 224 linears as 7 separate modules per layer (448 launches), as the reference "
+                                       "model calls them"),
                     roofline=roofline, tflops_linears=round(flops_rank * world / (ms * 1e-3) / 1e12, 1))
         if world == 1 and not args.no_sweep:
             line["gemm_sweep"] = gemm_sweep(dev, peaks)

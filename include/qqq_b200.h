@@ -57,6 +57,10 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
  *   x fp16 [M,K] row-major (K % 8 == 0, 16-byte aligned)  ->  q int8 [M,K], s1 fp32 [M]
  */
 int qqq_act_quant_sm100a(const void* x, void* q, void* s1, int prob_m, int prob_k, int dev, void* stream);
+/* Same, for x given as a column slice of a wider row-major matrix (row stride ldx halves, ldx % 8 == 0): lets the
+ * output slices of a merged QKV / gate-up GEMM be quantised in place, without a gather copy. */
+int qqq_act_quant_strided_sm100a(const void* x, long long ldx, void* q, void* s1, int prob_m, int prob_k, int dev,
+                                 void* stream);
 
 /* Library/ABI version (major*100 + minor) and the last error string of the calling thread. */
 int qqq_b200_version(void);

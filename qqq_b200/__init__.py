@@ -5,7 +5,7 @@ Public surface (mirrors the reference hot path only):
     mul(...), QuantLinear (alias QQQLinear)                                          <- QQQ.gptq.qlinear
 """
 from .ops import dynamic_quant, launch_count, qqq_gemm  # noqa: F401
-from .qlinear import QQQLinear, QuantLinear, mul, pack_int4_weights  # noqa: F401
+from .qlinear import QQQLinear, QuantLinear, merge_quant_linears, mul, pack_int4_weights  # noqa: F401
 
-__all__ = ["qqq_gemm", "dynamic_quant", "mul", "QuantLinear", "QQQLinear", "pack_int4_weights", "launch_count"]
+__all__ = ["qqq_gemm", "dynamic_quant", "mul", "QuantLinear", "QQQLinear", "pack_int4_weights", "merge_quant_linears", "launch_count"]
 __version__ = "0.1.0"

@@ -16,6 +16,7 @@ LIB_PATH = _HERE / "libqqq_b200.so"
 SYMBOLS = (
     "qqq_gemm_sm100a",
     "qqq_act_quant_sm100a",
+    "qqq_act_quant_strided_sm100a",
     "qqq_b200_version",
     "qqq_b200_last_error",
     "qqq_b200_launch_count",
@@ -48,6 +49,8 @@ def load() -> ctypes.CDLL:
     lib.qqq_gemm_sm100a.restype = ci
     lib.qqq_act_quant_sm100a.argtypes = [vp, vp, vp, ci, ci, ci, vp]
     lib.qqq_act_quant_sm100a.restype = ci
+    lib.qqq_act_quant_strided_sm100a.argtypes = [vp, ctypes.c_longlong, vp, vp, ci, ci, ci, vp]
+    lib.qqq_act_quant_strided_sm100a.restype = ci
     lib.qqq_b200_version.argtypes = []
     lib.qqq_b200_version.restype = ci
     lib.qqq_b200_last_error.argtypes = []

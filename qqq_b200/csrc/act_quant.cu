@@ -42,10 +42,11 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
 // NCH > 0: the row has at most NCH*256 chunks and lives in registers.  NCH == 0: any K, second pass re-reads x.
 template <int NCH>
 __global__ void __launch_bounds__(kQuantThreads)
-act_quant_kernel(const uint4* __restrict__ x, uint2* __restrict__ q, float* __restrict__ s1, int K8 /* K/8 */) {
+act_quant_kernel(const uint4* __restrict__ x, uint2* __restrict__ q, float* __restrict__ s1, int K8 /* K/8 */,
+                 int ldx8 /* row stride of x in 16-byte units */) {
   grid_dependency_wait();  // x is the preceding kernel's output (programmatic dependent launch)
   const int row = blockIdx.x;
-  const uint4* xr = x + (size_t)row * K8;
+  const uint4* xr = x + (size_t)row * ldx8;
   uint2* qr = q + (size_t)row * K8;
   constexpr int NC = NCH > 0 ? NCH : 1;
   uint4 cache[NC];
@@ -101,7 +102,8 @@ act_quant_kernel(const uint4* __restrict__ x, uint2* __restrict__ q, float* __re
 }
 
 template <int NCH>
-static cudaError_t launch_one(const uint4* xp, uint2* qp, float* sp, int M, int K8, cudaStream_t stream, bool pdl) {
+static cudaError_t launch_one(const uint4* xp, uint2* qp, float* sp, int M, int K8, int ldx8, cudaStream_t stream,
+                              bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(M);
   cfg.blockDim = dim3(kQuantThreads);
@@ -111,20 +113,22 @@ static cudaError_t launch_one(const uint4* xp, uint2* qp, float* sp, int M, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, act_quant_kernel<NCH>, xp, qp, sp, K8);
+  return cudaLaunchKernelEx(&cfg, act_quant_kernel<NCH>, xp, qp, sp, K8, ldx8);
 }
 
-cudaError_t launch_act_quant(const void* x, void* q, void* s1, int M, int K, cudaStream_t stream, bool pdl) {
+cudaError_t launch_act_quant(const void* x, long long ldx, void* q, void* s1, int M, int K, cudaStream_t stream,
+                             bool pdl) {
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   uint2* qp = reinterpret_cast<uint2*>(q);
   float* sp = reinterpret_cast<float*>(s1);
   const int K8 = K / 8;
+  const int ldx8 = (int)(ldx / 8);
   const int nch = (K8 + kQuantThreads - 1) / kQuantThreads;
-  if (nch <= 1) return launch_one<1>(xp, qp, sp, M, K8, stream, pdl);
-  if (nch <= 2) return launch_one<2>(xp, qp, sp, M, K8, stream, pdl);
-  if (nch <= 4) return launch_one<4>(xp, qp, sp, M, K8, stream, pdl);
-  if (nch <= 8) return launch_one<8>(xp, qp, sp, M, K8, stream, pdl);
-  return launch_one<0>(xp, qp, sp, M, K8, stream, pdl);
+  if (nch <= 1) return launch_one<1>(xp, qp, sp, M, K8, ldx8, stream, pdl);
+  if (nch <= 2) return launch_one<2>(xp, qp, sp, M, K8, ldx8, stream, pdl);
+  if (nch <= 4) return launch_one<4>(xp, qp, sp, M, K8, ldx8, stream, pdl);
+  if (nch <= 8) return launch_one<8>(xp, qp, sp, M, K8, ldx8, stream, pdl);
+  return launch_one<0>(xp, qp, sp, M, K8, ldx8, stream, pdl);
 }
 
 }  // namespace qqq

@@ -405,9 +405,11 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   return QQQ_OK;
 }
 
-int qqq_act_quant_sm100a(const void* x, void* q, void* s1, int prob_m, int prob_k, int dev, void* stream_) {
-  if (prob_m < 0 || prob_k <= 0 || prob_k % 8 != 0) {
-    set_err("act_quant: K must be a positive multiple of 8 (got m=%d k=%d)", prob_m, prob_k);
+int qqq_act_quant_strided_sm100a(const void* x, long long ldx, void* q, void* s1, int prob_m, int prob_k, int dev,
+                                 void* stream_) {
+  if (prob_m < 0 || prob_k <= 0 || prob_k % 8 != 0 || ldx < prob_k || ldx % 8 != 0) {
+    set_err("act_quant: K and the row stride must be positive multiples of 8, stride >= K (got m=%d k=%d ld=%lld)", prob_m,
+            prob_k, ldx);
     return QQQ_ERR_PROB_SHAPE;
   }
   if (prob_m == 0) return QQQ_OK;
@@ -426,13 +428,18 @@ int qqq_act_quant_sm100a(const void* x, void* q, void* s1, int prob_m, int prob_
   }
   DeviceGuard guard(dev);
   if (!guard.ok) return QQQ_ERR_CUDA;
-  cudaError_t e = qqq::launch_act_quant(x, q, s1, prob_m, prob_k, reinterpret_cast<cudaStream_t>(stream_), use_pdl());
+  cudaError_t e =
+      qqq::launch_act_quant(x, ldx, q, s1, prob_m, prob_k, reinterpret_cast<cudaStream_t>(stream_), use_pdl());
   if (e != cudaSuccess) {
     set_err("act_quant launch failed: %s", cudaGetErrorString(e));
     return QQQ_ERR_CUDA;
   }
   g_launches.fetch_add(1);
   return QQQ_OK;
+}
+
+int qqq_act_quant_sm100a(const void* x, void* q, void* s1, int prob_m, int prob_k, int dev, void* stream_) {
+  return qqq_act_quant_strided_sm100a(x, prob_k, q, s1, prob_m, prob_k, dev, stream_);
 }
 
 }  // extern "C"

@@ -173,6 +173,7 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 // ---- host-side declarations (qqq_c_api.cu) ----------------------------------------------------------
-cudaError_t launch_act_quant(const void* x, void* q, void* s1, int M, int K, cudaStream_t stream, bool pdl);
+cudaError_t launch_act_quant(const void* x, long long ldx, void* q, void* s1, int M, int K, cudaStream_t stream,
+                             bool pdl);
 
 }  // namespace qqq

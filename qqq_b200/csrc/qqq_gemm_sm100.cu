@@ -495,10 +495,18 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 dp[(size_t)i * ldn] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]);
               }
             }
-          } else {
+          } else {  // ragged last chunk: same arithmetic, only the store is predicated
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (mb + i < rows) dp[(size_t)i * ldn] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * s1_sm[mb + i]);
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 sv = s4[g4];
+              const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = 4 * g4 + j;
+                const __half h = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]);
+                if (mb + i < rows) dp[(size_t)i * ldn] = h;
+              }
+            }
           }
         } else {
           int* __restrict__ slot = ccol + (size_t)(ticket * m_pad + m0 + mb) * ldn;

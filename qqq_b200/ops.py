@@ -78,14 +78,18 @@ def dynamic_quant(x: torch.Tensor):
     (qlinear_marlin.py:265-268), as ONE kernel.  x fp16 [M,K] -> (int8 [M,K], fp32 [M,1])."""
     if x.dtype != torch.float16 or not x.is_cuda:
         raise RuntimeError("dynamic_quant expects a CUDA fp16 tensor (qqq_b200 has no CPU path).")
-    x = x.contiguous()
     M, K = x.shape
+    # a column slice of a wider row-major matrix (output of a merged GEMM) is quantised in place
+    strided_ok = x.stride(1) == 1 and x.stride(0) >= K and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0
+    if not strided_ok:
+        x = x.contiguous()
     q = torch.empty((M, K), dtype=torch.int8, device=x.device)
     s = torch.empty((M, 1), dtype=torch.float32, device=x.device)
     if M == 0:
         return q, s
     dev = x.get_device()
-    err = _lib.load().qqq_act_quant_sm100a(_ptr(x), _ptr(q), _ptr(s), M, K, dev, torch.cuda.current_stream(dev).cuda_stream)
+    err = _lib.load().qqq_act_quant_strided_sm100a(_ptr(x), x.stride(0), _ptr(q), _ptr(s), M, K, dev,
+                                                   torch.cuda.current_stream(dev).cuda_stream)
     if err != 0:
         raise RuntimeError(f"qqq_act_quant_sm100a failed (rc={err}): {_lib.last_error()}")
     return q, s

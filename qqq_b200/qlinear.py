@@ -194,6 +194,35 @@ class QuantLinear(nn.Module):
         return D
 
 
+def merge_quant_linears(mods) -> QuantLinear:
+    """Merge QuantLinears that consume the SAME input (q/k/v, gate/up) into one module whose output is the
+    concatenation of theirs along the feature dim: one activation quant and one GEMM instead of len(mods) of each.
+
+    Pure concatenation of the packed tensors along N — no repack: every 64-channel block of `B` is 128
+    consecutive words of a row and the scale permutations act inside 32/64-channel blocks, so column blocks of
+    different linears can simply be laid side by side.  Outputs are bit-identical to the separate modules
+    (each output column depends only on its own weight column and the shared, identically quantised input).
+    """
+    mods = list(mods)
+    m0 = mods[0]
+    assert all(m.infeatures == m0.infeatures and m.group_size == m0.group_size and m.bits == m0.bits for m in mods)
+    assert all(m.outfeatures % 64 == 0 for m in mods)
+    has_bias = any(m.bias is not None for m in mods)
+    gs = m0.group_size if m0.per_group else -1
+    out = QuantLinear(m0.bits, gs, m0.infeatures, sum(m.outfeatures for m in mods), bias=has_bias)
+    dev = m0.B.device
+    out.B = torch.cat([m.B for m in mods], dim=1).contiguous()
+    out.s_channel = torch.cat([m.s_channel for m in mods], dim=1).contiguous()
+    out.s_group = torch.cat([m.s_group for m in mods], dim=1).contiguous() if m0.per_group else m0.s_group
+    if has_bias:
+        out.bias = torch.cat([m.bias if m.bias is not None else torch.zeros(m.outfeatures, dtype=torch.half, device=dev)
+                              for m in mods]).contiguous()
+    out.workspace = torch.zeros(max(out.outfeatures // 128 * 16, 16), dtype=torch.int32, device=dev)
+    out.reduce_buffer = torch.zeros((out.max_par * 64, out.outfeatures), dtype=torch.int32, device=dev)
+    out.split_sizes = [m.outfeatures for m in mods]
+    return out
+
+
 QQQLinear = QuantLinear
 
-__all__ = ["QuantLinear", "QQQLinear", "mul", "pack_int4_weights"]
+__all__ = ["QuantLinear", "QQQLinear", "mul", "pack_int4_weights", "merge_quant_linears"]

@@ -87,3 +87,25 @@ def test_forward_without_gpu_fails_loudly():
     ql = QuantLinear(4, -1, 128, 128, bias=False)
     with pytest.raises(RuntimeError, match="no CPU path"):
         ql(torch.zeros(2, 128, dtype=torch.float16))
+
+
+def test_merge_quant_linears_is_pure_concatenation():
+    from qqq_b200 import merge_quant_linears
+
+    mods = []
+    for path in [p for p in PACK if "K256_N256" in p]:
+        mods.append(_module_from_golden(np.load(path)))
+    pc = [m for m in mods if not m.per_group]
+    a = pc[0]
+    b = QuantLinear(4, -1, 256, 128, bias=False)
+    b.B.copy_(torch.randint(-2**31, 2**31 - 1, b.B.shape, dtype=torch.int32))
+    b.s_channel.copy_(torch.rand(1, 128))
+    m = merge_quant_linears([a, b])
+    assert m.outfeatures == 384 and m.B.shape == (16, 768)
+    assert torch.equal(m.B[:, :512], a.B) and torch.equal(m.B[:, 512:], b.B)
+    assert torch.equal(m.s_channel[:, :256], a.s_channel) and torch.equal(m.s_channel[:, 256:], b.s_channel)
+    # the merged packed tensor decodes to the side-by-side weight matrices
+    W = O.weights_int8(m.B.numpy(), None)
+    assert np.array_equal(W[:, :256], O.weights_int8(a.B.numpy(), None))
+    assert np.array_equal(W[:, 256:], O.weights_int8(b.B.numpy(), None))
+    assert m.bias is not None and torch.equal(m.bias[:256], a.bias) and int(m.bias[256:].abs().sum()) == 0

@@ -1,0 +1,70 @@
+"""GPU: the module-level path (QuantLinear.forward = fused act-quant + tcgen05 GEMM through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import qqq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _module(p, K, N, gs, dev="cuda:0"):
+    import qqq_b200
+
+    ql = qqq_b200.QuantLinear(4, gs, K, N, bias=False)
+    ql.B.copy_(torch.from_numpy(p["B"]))
+    ql.s_channel.copy_(torch.from_numpy(p["s2"]))
+    if gs != -1:
+        ql.s_group.copy_(torch.from_numpy(p["s3"]))
+    return ql.to(dev)
+
+
+@pytest.mark.parametrize("M,K,N,gs", [(1, 4096, 4096, -1), (9, 512, 256, 128), (300, 1024, 384, -1)])
+def test_forward_bit_exact_vs_oracle(M, K, N, gs):
+    """Includes BASELINE config 1 (M=1, K=N=4096, per-channel) on the GPU path."""
+    p = O.make_problem(M, K, N, gs, seed=4)
+    ql = _module(p, K, N, gs)
+    y = ql(torch.from_numpy(p["x"]).cuda()).cpu().numpy()
+    A8, s1 = O.dynamic_quant(p["x"], cuda_semantics=True)
+    ref = O.qqq_gemm_oracle(A8, p["B"], s1, p["s2"], p["s3"])
+    assert np.array_equal(y.view(np.uint16), ref.view(np.uint16))
+
+
+def test_forward_keeps_leading_dims_and_bias():
+    p = O.make_problem(6, 256, 128, -1, seed=2)
+    ql = _module(p, 256, 128, -1)
+    ql.bias = torch.full((128,), 0.5, dtype=torch.half, device="cuda:0")
+    x = torch.from_numpy(p["x"]).cuda().reshape(2, 3, 256)
+    y = ql(x)
+    assert y.shape == (2, 3, 128)
+    ql.bias = None
+    y0 = ql(x)
+    assert torch.equal(y, y0 + 0.5)
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_merged_linears_bit_identical_to_separate(gs):
+    import qqq_b200
+
+    K = 1024
+    ps = [O.make_problem(40, K, n, gs, seed=s) for n, s in ((256, 1), (128, 2), (384, 3))]
+    x = torch.from_numpy(ps[0]["x"]).cuda()
+    mods = [_module(p, K, p["B"].shape[1] // 2, gs) for p in ps]
+    merged = qqq_b200.merge_quant_linears(mods)
+    y = merged(x)
+    parts = torch.split(y, merged.split_sizes, dim=-1)
+    for m, part in zip(mods, parts):
+        assert torch.equal(m(x), part)
+
+
+def test_graph_capture_replays_the_same_bits():
+    from qqq_b200 import graph
+
+    p = O.make_problem(32, 1024, 512, 128, seed=6)
+    ql = _module(p, 1024, 512, 128)
+    x = torch.from_numpy(p["x"]).cuda()
+    eager = ql(x).clone()
+    g = graph.capture(lambda t: ql(t), x)
+    out = g(x).clone()
+    out2 = g(x * 1).clone()
+    assert torch.equal(eager, out) and torch.equal(eager, out2)
