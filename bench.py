@@ -209,12 +209,15 @@ def forward_chain_merged(mlayers, h, world):
     return h
 
 
+GEMM_NAMES = ("q", "k", "v", "o", "gate", "up", "down")
+
+
 def gemm_only_chain(mlayers, qin):
     """The GEMM launches of a step alone, on pre-quantised inputs (for the roofline figure of the dominant kernel)."""
     import qqq_b200
 
     for m in mlayers:
-        for name in ("qkv", "o", "gate_up", "down"):
+        for name in GEMM_NAMES:
             ql = m[name]
             A8, s1, D = qin[(ql.infeatures, ql.outfeatures)]
             qqq_b200.qqq_gemm(A8, ql.B, ql.reduce_buffer, D, s1, ql.s_channel, ql.s_group, ql.workspace, -1, -1, -1, 16)
@@ -360,9 +363,9 @@ def main():
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
     M = MODEL["seq"] * MODEL["batch"]
-    cfg = dict(workload="llama-2-7b prefill seq=1024 batch=1: all 224 quantized linears (per-channel W4A8); q/k/v and "
-                        "gate/up merged by concatenating their packed tensors (bit-identical outputs): per layer 4 x "
-                        "(per-token act-quant + W4A8 GEMM); random-init weights",
+    cfg = dict(workload="llama-2-7b prefill seq=1024 batch=1: all 224 quantized linears (per-channel W4A8), called module "
+                        "by module as the reference model does: per layer 7 x (per-token act-quant + W4A8 GEMM); "
+                        "random-init weights",
                global_batch=MODEL["batch"], seq_len=MODEL["seq"], parallelism=f"tp{world}" if world > 1 else "single",
                l2="inputs larger than L2: 3.2 GB of packed weights stream from HBM every step")
 
@@ -400,16 +403,24 @@ def main():
     # --- device-resident throughput (value): a step's launches are replayed from one CUDA graph ---
     from qqq_b200 import graph as qgraph
 
-    mlayers = merge_layers(layers)
+    def max_over_ranks(ms_local):
+        t = torch.tensor([ms_local], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # headline: the 224 linears called module by module like the reference model (7 activation quants + 7 GEMMs per layer)
     l0 = qqq_b200.launch_count()
-    forward_chain_merged(mlayers, x_dev, world)
+    forward_chain(layers, x_dev, world)
     launches_per_step = qqq_b200.launch_count() - l0
-    graphed = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
+    graphed = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
     with ClockSampler(local_rank) as cs:
-        ms = timed(lambda: graphed(x_dev), args.steps, args.warmup, barrier)
-    # the same 224 linears called module by module like the reference model (7 GEMMs + 7 activation quants per layer)
-    graphed_sep = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
-    ms_sep = timed(lambda: graphed_sep(x_dev), args.steps, args.warmup, barrier)
+        ms = max_over_ranks(timed(lambda: graphed(x_dev), args.steps, args.warmup, barrier))
+    value = M / (ms * 1e-3)
+    # the same weights with q/k/v and gate/up merged: 4 activation quants + 4 GEMMs per layer
+    mlayers = merge_layers(layers)
+    graphed_mrg = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
+    ms_mrg = max_over_ranks(timed(lambda: graphed_mrg(x_dev), args.steps, args.warmup, barrier))
     # --- end to end: pinned host input -> H2D -> 224 linears -> D2H of the result, every step ---
     def e2e_step():
         h = graphed(x_host)  # pinned host -> static device input (H2D), graph replay
@@ -418,7 +429,7 @@ def main():
     # the same step through the eager public API (no graph), for the record
     def eager_step():
         x_dev.copy_(x_host, non_blocking=True)
-        out_host.copy_(forward_chain_merged(mlayers, x_dev, world), non_blocking=True)
+        out_host.copy_(forward_chain(layers, x_dev, world), non_blocking=True)
 
     ms_eager = timed(eager_step, args.steps, args.warmup, barrier)
 
@@ -430,29 +441,29 @@ def main():
 
     # --- dominant kernel alone: the 224 GEMM launches on pre-quantised inputs ---
     qin = {}
-    for name in ("qkv", "o", "gate_up", "down"):
-        ql = mlayers[0][name]
+    for name in GEMM_NAMES:
+        ql = layers[0][name]
         key = (ql.infeatures, ql.outfeatures)
         if key not in qin:
             A8 = torch.randint(-127, 128, (M, key[0]), dtype=torch.int8, device=dev)
             qin[key] = (A8, torch.full((M, 1), 0.03, device=dev), torch.empty(M, key[1], dtype=torch.float16, device=dev))
     def _gemm_chain(x):
-        gemm_only_chain(mlayers, qin)
+        gemm_only_chain(layers, qin)
         return x
 
     graphed_gemm = qgraph.capture(_gemm_chain, x_dev)
     ms_gemm = timed(lambda: graphed_gemm(x_dev), args.steps, args.warmup, barrier)
-    n_gemm = MODEL["layers"] * 4
+    n_gemm = MODEL["layers"] * len(GEMM_NAMES)
     flops_rank = model_flops(M) / world
     int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
     achieved = flops_rank / (ms_gemm * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01", "ncu", "traffic.json")
     if world == 1 and os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full captures
-        traffic = json.load(open(tpath)).get("llama2_7b_prefill_m1024_merged", {}).get("avg_per_launch")
+        traffic = json.load(open(tpath)).get("llama2_7b_prefill_m1024", {}).get("avg_per_launch")
     roofline = dict(bound="tensor", kernel="qqq_gemm_kernel<per-channel> (tcgen05 kind::i8)", achieved=round(achieved, 1),
                     peak=round(int8_peak, 1), unit="TFLOP/s", frac=round(achieved / int8_peak, 4), traffic=traffic,
-                    traffic_note="dram__bytes_read+write per launch, mean over the 4 GEMMs of a layer (ncu, "
+                    traffic_note="dram__bytes_read+write per launch, mean over the 7 GEMMs of a layer (ncu, "
                                  "profiles/r01/ncu/traffic.json); below the algorithmic bytes because A8 and D stay in L2",
                     peak_source=f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['source']}); int8 dense = 2x bf16 "
                                 "on sm_100a; UTCIMMA-only microbenchmark on this pool measured 4428 TOP/s burst "
@@ -472,9 +483,9 @@ def main():
                                  f"{ms_eager:.3f} ms/step"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     launch_mode="cuda-graph replay of the per-step launches",
-                    unmerged=dict(ms_per_step=round(ms_sep, 4), value=round(M / (ms_sep * 1e-3), 1),
-                                  note="same 224 linears as 7 separate modules per layer (448 launches), as the reference "
-                                       "model calls them"),
+                    merged=dict(ms_per_step=round(ms_mrg, 4), value=round(M / (ms_mrg * 1e-3), 1),
+                                note="same weights with q/k/v and gate/up merged by concatenating their packed tensors "
+                                     "(qqq_b200.merge_quant_linears, bit-identical outputs): 4 act-quants + 4 GEMMs per layer"),
                     roofline=roofline, tflops_linears=round(flops_rank * world / (ms * 1e-3) / 1e12, 1))
         if world == 1 and not args.no_sweep:
             line["gemm_sweep"] = gemm_sweep(dev, peaks)
