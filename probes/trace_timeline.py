@@ -46,6 +46,11 @@ stats("mma: interval between unit issues", np.diff(M5))
 stats("mma: issue block duration (TR6-TR5)", M6 - M5)
 stats("epilogue: drain (TR8-TR7)", E8 - E7)
 stats("epilogue: total incl fixup (TR11-TR7)", E11 - E7)
+E13, E14 = rel(13), rel(14)
+if len(E13) and len(E13) == len(E14):
+    stats("epilogue warp 0: chunk convert+store (TR14-TR13)", E14 - E13)
+    if len(E13) > 1:
+        stats("epilogue warp 0: wait for next chunk's tcgen05.ld (TR13[i+1]-TR14[i])", E13[1:] - E14[:-1])
 idx = np.nonzero(t[2])[0]
 u2 = t[2, idx].astype(np.int64) - t0; u3 = t[3, idx].astype(np.int64) - t0; u10 = t[10, idx].astype(np.int64) - t0; u4 = t[4, idx].astype(np.int64) - t0
 stats("unpack(q0 warps): LDS issue + wait aempty (TR3-TR2)", u3 - u2)

@@ -44,7 +44,8 @@ template <int NCH>
 __global__ void __launch_bounds__(kQuantThreads)
 act_quant_kernel(const uint4* __restrict__ x, uint2* __restrict__ q, float* __restrict__ s1, int K8 /* K/8 */,
                  int ldx8 /* row stride of x in 16-byte units */) {
-  grid_dependency_wait();  // x is the preceding kernel's output (programmatic dependent launch)
+  grid_launch_dependents();  // the GEMM that consumes q/s1 may start its prologue and weight prefetch right away
+  grid_dependency_wait();    // x is the preceding kernel's output (programmatic dependent launch)
   const int row = blockIdx.x;
   const uint4* xr = x + (size_t)row * ldx8;
   uint2* qr = q + (size_t)row * K8;

@@ -75,6 +75,15 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // Programmatic dependent launch: block until the grid this launch depends on has completed and its memory is
 // visible (no-op when the kernel was not launched with the programmatic-serialization attribute).
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Let the NEXT kernel in the stream (if it was launched with the programmatic-serialization attribute) be scheduled
+// as soon as every CTA of this grid has passed this point and SM resources free up, instead of after this grid has
+// completed: its prologue (barrier init, TMEM allocation, weight prefetch) then runs under this grid's tail.  The
+// dependent still blocks in griddepcontrol.wait until this grid has completed and flushed, so no data hazard arises.
+__device__ __forceinline__ void grid_launch_dependents() {
+#ifndef QQQ_NO_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // ---- TMEM -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {

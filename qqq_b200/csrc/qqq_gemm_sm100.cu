@@ -111,10 +111,17 @@ __device__ __forceinline__ void unpack_pc(uint32_t w, uint32_t& b0, uint32_t& b1
 // rounding is identical.  We add 1280 (0x6500) instead of the reference's 1152 (0x6480): 1280 = 1024+256, so
 // the low mantissa byte is RNE((v-8)*s) mod 256, i.e. already two's complement — the reference's final
 // `^ 0x80808080` disappears.  Identical for every |RNE((v-8)*s)| <= 128, which pack() guarantees (:209-217).
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {  // (a & b) | c
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 __device__ __forceinline__ uint32_t unpack_pg4(uint32_t w, uint32_t s2h) {
   // w holds the 4 nibbles of ONE channel at bits [0,4) [16,20) (k r0,r1) and [4,8) [20,24) (k r2,r3)
-  uint32_t lo = (w & 0x000F000Fu) | 0x64006400u;  // (1024 + v_r0, 1024 + v_r1)
-  uint32_t hi = (w & 0x00F000F0u) | 0x64006400u;  // (1024 + 16 v_r2, 1024 + 16 v_r3)
+  // (w & mask) | 0x6400 as ONE three-input LOP3 with both constants in registers: with two immediates the
+  // compiler emits an AND and an OR, and the ALU pipe (not the fp16 pipe) becomes the bound of the whole kernel
+  uint32_t lo = and_or(w, 0x000F000Fu, 0x64006400u);  // (1024 + v_r0, 1024 + v_r1)
+  uint32_t hi = and_or(w, 0x00F000F0u, 0x64006400u);  // (1024 + 16 v_r2, 1024 + 16 v_r3)
   const uint32_t k1032 = 0x64086408u, k1_16 = 0x2C002C00u, km72 = 0xD480D480u, k1280 = 0x65006500u;
   __half2 x01 = __hsub2(*reinterpret_cast<__half2*>(&lo), *reinterpret_cast<const __half2*>(&k1032));
   __half2 x23 = __hfma2(*reinterpret_cast<__half2*>(&hi), *reinterpret_cast<const __half2*>(&k1_16),
@@ -168,6 +175,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int n_seg = sched.num_segments();
   QQQ_TR_INIT();
 
+  grid_launch_dependents();
   if (warp == 0) {
     // barrier init spread over the lanes of warp 0
     if (lane == 0) {
@@ -397,6 +405,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const size_t ldn = (size_t)p.N;
     grid_dependency_wait();  // s1 comes from the preceding kernel; D / C / lock words may still be in use by it
     int staged_mt = -1;
+#ifdef QQQ_TRACE
+    int echunk = 0;
+#endif
     for (int seg = 0; seg < n_seg; ++seg) {
       int tile, kb0, kb1;
       sched.segment(seg, tile, kb0, kb1);
@@ -470,16 +481,15 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       };
       if (others > 0 && 16 * eh < rows) fetch_partials(16 * eh, pre);
 
-      for (int mb = 16 * eh; mb < rows; mb += mstep) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(tmem_d + mb, r);
-        tmem_wait_ld();
+      // One 16-token chunk of this lane's channel: add the published partials (finisher), then either scale + store
+      // fp16 rows of D or publish the int32 partial.
+      auto process = [&](uint32_t(&r)[16], int mb) {
         if (others > 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] += (uint32_t)pre[i];
           if (mb + mstep < rows) fetch_partials(mb + mstep, pre);
         }
-        if (!n_ok) continue;
+        if (!n_ok) return;
         const bool full16 = mb + 16 <= rows;
         if (finish) {
           __half* __restrict__ dp = dcol + (size_t)(m0 + mb) * ldn;
@@ -518,6 +528,28 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             for (int i = 0; i < 16; ++i)
               if (mb + i < rows) slot[(size_t)i * ldn] = (int)r[i];
           }
+        }
+      };
+      // Software-pipelined drain: the TMEM load of the next chunk is in flight while this one is converted and
+      // stored (a tcgen05.ld round trip is ~230 cycles with all epilogue warps active; TMEM reads run at 64 B/clk).
+      {
+        uint32_t ra[16], rb[16];
+        int mb = 16 * eh;
+        if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
+        while (mb < rows) {
+          tmem_wait_ld();
+          if (epi_tid == 0) QQQ_TR(13, echunk);
+          const int mb2 = mb + mstep;
+          if (mb2 < rows) tmem_ld_32x32b_x16(tmem_d + mb2, rb);
+          process(ra, mb);
+          if (epi_tid == 0) QQQ_TR(14, echunk++);
+          if (mb2 >= rows) break;
+          tmem_wait_ld();
+          if (epi_tid == 0) QQQ_TR(13, echunk);
+          mb = mb2 + mstep;
+          if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
+          process(rb, mb2);
+          if (epi_tid == 0) QQQ_TR(14, echunk++);
         }
       }
       tc_fence_before();
