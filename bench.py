@@ -359,6 +359,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-merged", action="store_true", help="skip the merged QKV / gate-up variant (profiler runs)")
     args = ap.parse_args()
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
@@ -418,9 +419,12 @@ def main():
         ms = max_over_ranks(timed(lambda: graphed(x_dev), args.steps, args.warmup, barrier))
     value = M / (ms * 1e-3)
     # the same weights with q/k/v and gate/up merged: 4 activation quants + 4 GEMMs per layer
-    mlayers = merge_layers(layers)
-    graphed_mrg = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
-    ms_mrg = max_over_ranks(timed(lambda: graphed_mrg(x_dev), args.steps, args.warmup, barrier))
+    ms_mrg = None
+    if not args.no_merged:
+        mlayers = merge_layers(layers)
+        graphed_mrg = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
+        ms_mrg = max_over_ranks(timed(lambda: graphed_mrg(x_dev), args.steps, args.warmup, barrier))
+        del graphed_mrg, mlayers
     # --- end to end: pinned host input -> H2D -> 224 linears -> D2H of the result, every step ---
     def e2e_step():
         h = graphed(x_host)  # pinned host -> static device input (H2D), graph replay
@@ -483,9 +487,10 @@ def main():
                                  f"{ms_eager:.3f} ms/step"),
                     gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                     launch_mode="cuda-graph replay of the per-step launches",
-                    merged=dict(ms_per_step=round(ms_mrg, 4), value=round(M / (ms_mrg * 1e-3), 1),
-                                note="same weights with q/k/v and gate/up merged by concatenating their packed tensors "
-                                     "(qqq_b200.merge_quant_linears, bit-identical outputs): 4 act-quants + 4 GEMMs per layer"),
+                    merged=None if ms_mrg is None else dict(
+                        ms_per_step=round(ms_mrg, 4), value=round(M / (ms_mrg * 1e-3), 1),
+                        note="same weights with q/k/v and gate/up merged by concatenating their packed tensors "
+                             "(qqq_b200.merge_quant_linears, bit-identical outputs): 4 act-quants + 4 GEMMs per layer"),
                     roofline=roofline, tflops_linears=round(flops_rank * world / (ms * 1e-3) / 1e12, 1))
         if world == 1 and not args.no_sweep:
             line["gemm_sweep"] = gemm_sweep(dev, peaks)

@@ -220,7 +220,8 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   // (long latency, ~160 KB in flight); with several token tiles they mostly hit L2 (~64 KB).  The token ring
   // (L2-resident data) takes the rest, at least 3 and at most 6 stages.
   const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
-  const int budget = kMaxSmemBytes - 1024 - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
+  const int budget =
+      kMaxSmemBytes - 1024 - kEpiStageBytes - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
   const int target_w = p.m_tiles == 1 ? 163840 : 65536;
   int nsw = (target_w + stage_w - 1) / stage_w;
   nsw = nsw < 3 ? 3 : (nsw > kMaxStages ? kMaxStages : nsw);
@@ -246,22 +247,26 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   }
   p.stages_t = nst;
   static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
-  // decode-size tiles and the ALU-heavy per-group rescale: 3 unpack groups + 4 epilogue warps; large per-channel
-  // tiles: the accumulator drain is the exposed part, so 2 unpack groups + 8 epilogue warps.
-  const int g_auto = (grouped || p.n_tok <= 64) ? 3 : 2;
+  // decode-size tiles: 3 unpack groups + 4 epilogue warps; from 128 tokens up the accumulator drain is the exposed
+  // part: 2 unpack groups + 8 epilogue warps (measured for both modes: the per-group rescale is bound by the fp16
+  // pipe of the sub-partition, which a third warp on the same sub-partition cannot widen).
+  const int g_auto = p.n_tok <= 64 ? 3 : 2;
+  (void)grouped;
   p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
   p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
 
   int grid = sm_count;
   if ((long long)grid > units) grid = (int)units;
   // Schedule.  Whole tiles go round the CTAs in waves; the remainder tiles that would leave SMs idle in a last
-  // partial wave are instead cut along K over all CTAs (stream-K) when the caller's scratch allows it: a split tile
-  // needs one slot of C (m_tiles*n_tok rows of the 64*max_par) per contributor but the last, and one lock word.
+  // partial wave are instead cut along K over all CTAs (stream-K) when the caller's scratch allows it: C (64*max_par
+  // rows of N int32) holds compact [n_tok][128] partial tiles, block index = ticket*a_tiles + tile, i.e. one set of
+  // a_tiles blocks per contributor but the last; plus one lock word per tile.
   const long long whole_per_cta = tiles / grid;
   const long long rem = tiles - whole_per_cta * grid;
   long long a_tiles = 0, a_upc = 1;
   if (rem > 0 && has_scratch && tiles <= (long long)(N / 128) * max_par && (double)rem / grid < 0.92) {
-    const long long slot_rows = (long long)p.m_tiles * p.n_tok, c_rows = 64ll * max_par;
+    const long long tile_ints = (long long)p.n_tok * kTileN;  // one partial tile
+    const long long c_ints = 64ll * max_par * N;              // capacity of C
     auto parts_max = [&](long long upc) { return (upc % p.k_units == 0) ? 1ll : (p.k_units - 1) / upc + 2; };
     // (1) cut only the remainder tiles, over all CTAs, ahead of the whole tiles (fix-up hidden behind the rest)
     const long long upc_rem = (rem * p.k_units + grid - 1) / grid;
@@ -270,10 +275,10 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     const long long upc_all = (units + grid - 1) / grid;
     // (1) multiplies the contributors per tile (and with them the partial-tile traffic of the fix-up), so it is
     // used for decode-size tiles only; measured: wins at n_tok <= 32, loses from 64 tokens up.
-    if (p.n_tok <= 32 && (parts_max(upc_rem) - 1) * slot_rows <= c_rows) {
+    if (p.n_tok <= 32 && (parts_max(upc_rem) - 1) * rem * tile_ints <= c_ints) {
       a_tiles = rem;
       a_upc = upc_rem;
-    } else if ((parts_max(upc_all) - 1) * slot_rows <= c_rows) {
+    } else if ((parts_max(upc_all) - 1) * tiles * tile_ints <= c_ints) {
       a_tiles = tiles;
       a_upc = upc_all;
     }
@@ -348,8 +353,9 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
     set_err("per-group needs K %% 128 == 0");
     return QQQ_ERR_PROB_SHAPE;
   }
-  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(s3)) & 15) {
-    set_err("A, B and s3 must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(D) |
+       reinterpret_cast<uintptr_t>(s3)) & 15) {
+    set_err("A, B, D and s3 must be 16-byte aligned");
     return QQQ_ERR_PROB_SHAPE;
   }
   const DeviceInfo* di = device_info(dev);
@@ -388,7 +394,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   p.hint_b = p.m_tiles == 1 ? kEvictFirst : kEvictNormal;
   p.hint_a = kEvictLast;
 
-  CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap_a, tmap_b, tmap_d;
   if (!encode_2d(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, A, (uint64_t)K, (uint64_t)M, (uint64_t)K, kBlockK,
                  (uint32_t)p.n_tok, CU_TENSOR_MAP_SWIZZLE_128B))
     return QQQ_ERR_CUDA;
@@ -396,7 +402,12 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
                  2 * kTileN, 8 * p.ksub, CU_TENSOR_MAP_SWIZZLE_NONE))
     return QQQ_ERR_CUDA;
 
-  cudaError_t e = launch_gemm(tmap_a, tmap_b, p, grouped, grid, dev, stream, use_pdl());
+  // D as a TMA-store target: [M rows][N fp16], boxes of 16 tokens x 128 channels (clipped at M and N)
+  if (!encode_2d(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, kTileN, 16,
+                 CU_TENSOR_MAP_SWIZZLE_NONE))
+    return QQQ_ERR_CUDA;
+
+  cudaError_t e = launch_gemm(tmap_a, tmap_b, tmap_d, p, grouped, grid, dev, stream, use_pdl());
   if (e != cudaSuccess) {
     set_err("kernel launch failed: %s", cudaGetErrorString(e));
     return QQQ_ERR_CUDA;

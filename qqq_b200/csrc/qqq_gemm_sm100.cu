@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t unpack_pg4(uint32_t w, uint32_t s2h) {
 template <bool GROUPED>
 __global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -150,7 +150,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int NA = min(kMaxASlots, (512 - tmem_a0) / (32 * KSUB));
   const int tok_bytes = p.n_tok * 128;      // one sub-block of tokens
   const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
-  uint8_t* sT = smem;
+  uint8_t* sStage = smem;                   // epilogue staging: 2 groups x 2 tiles of [16][128] fp16
+  uint8_t* sT = sStage + kEpiStageBytes;
   uint8_t* sW = sT + NST * stage_t;
   uint8_t* sS = sW + NSW * stage_w;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSW * stage_s);
@@ -181,6 +182,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
+      tma_prefetch_desc(&tmap_d);
     }
     for (int i = lane; i < NSW; i += 32) {
       mbar_init(bar_fullw + 8 * i, 1);
@@ -401,8 +403,14 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int epi_tid = threadIdx.x - epi_warp0 * 32;
     const int eh = (warp - epi_warp0) >> 2;  // which of the n_epi/4 warps of this quadrant: takes every (n_epi/4)-th chunk
     const int mstep = 16 * (n_epi >> 2);
-    const int m_pad = p.m_tiles * p.n_tok;  // rows of one split-K slot in C
-    const size_t ldn = (size_t)p.N;
+    // D leaves through shared memory: the 4 quadrant warps of a group transpose one 16-token chunk into a
+    // [16 tokens][128 channels] fp16 tile (row = 256 B) and one thread hands it to TMA (coalesced full-line writes;
+    // rows past M and channels past N are clipped by the tensor map).  Two tiles per group, alternating.
+    uint8_t* stg = sStage + eh * (2 * kStageD);
+    const uint32_t grp_bar = 2 + eh;             // named barrier of this group's 4 warps
+    const bool issuer = (q == 0) && (lane == 0); // bulk async-groups are per thread: always the same one
+    int sbuf = 0;
+    const size_t tile_ints = (size_t)p.n_tok * kTileN;  // one partial tile in C
     grid_dependency_wait();  // s1 comes from the preceding kernel; D / C / lock words may still be in use by it
     int staged_mt = -1;
 #ifdef QQQ_TRACE
@@ -422,8 +430,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // contributors of a phase-A tile: the CTAs whose slice [b*a_upc, (b+1)*a_upc) meets the tile's units
       const int parts = whole ? 1 : (tile * KU + KU - 1) / p.a_upc - (tile * KU) / p.a_upc + 1;
       const float s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;
-      __half* __restrict__ dcol = p.D + n;
-      int* __restrict__ ccol = p.C + n;
+      // Partial tiles of split-K live in C as compact [n_tok][128] int32 blocks, block index =
+      // (ticket * a_tiles + tile): a chunk's 16 rows are 512 B apart, so the 16 stores / loads of a lane use one base
+      // register and immediate offsets (no serial address chain), and each of them is one full 128-byte line per warp.
+      int* __restrict__ cbase = p.C + (size_t)tile * tile_ints + 32 * q + lane;
+      const size_t ticket_stride = (size_t)p.a_tiles * tile_ints;  // split tiles are tiles [0, a_tiles)
 
       // per-token scales of this token tile -> smem (once per tile change), so the store loop has no global loads
       if (mt != staged_mt) {
@@ -439,7 +450,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok + ((uint32_t)(32 * q) << 16);
 
       // Split-K tiles: contributors take a ticket on the tile's lock word (low half = tickets, high half = partials
-      // published).  Tickets 0..parts-2 publish their int32 partial tile to slot[ticket] of C (plain coalesced
+      // published).  Tickets 0..parts-2 publish their int32 partial tile to block[ticket] of C (plain coalesced
       // stores); the last ticket keeps its partial in TMEM, waits until the others are published (they arrived
       // earlier, so this is normally immediate), adds them and finishes the tile.  Integer sums: exact in any order.
       int ticket = 0;
@@ -461,77 +472,59 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const bool finish = whole || ticket == parts - 1;  // this CTA writes D for the tile
       const int others = (!whole && finish) ? parts - 1 : 0;  // published partial tiles the finisher adds
 
-      // partial sums published by the other contributors, prefetched one 16-row chunk ahead
+      // partial sums published by the other contributors, prefetched one 16-row chunk ahead (rows past `rows`
+      // of a published block hold sums of zero-filled tokens, i.e. zeros: no predication needed)
       int pre[16];
       auto fetch_partials = [&](int mb, int* acc) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0;
-        if (!n_ok) return;
         for (int pp = 0; pp < others; ++pp) {
-          const int* __restrict__ src = ccol + (size_t)(pp * m_pad + m0 + mb) * ldn;
-          if (mb + 16 <= rows) {
+          const int* __restrict__ src = cbase + (size_t)pp * ticket_stride + (size_t)mb * kTileN;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] += __ldcg(src + (size_t)i * ldn);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (mb + i < rows) acc[i] += __ldcg(src + (size_t)i * ldn);
-          }
+          for (int i = 0; i < 16; ++i) acc[i] += __ldcg(src + i * kTileN);
         }
       };
       if (others > 0 && 16 * eh < rows) fetch_partials(16 * eh, pre);
 
-      // One 16-token chunk of this lane's channel: add the published partials (finisher), then either scale + store
-      // fp16 rows of D or publish the int32 partial.
+      // One 16-token chunk of this lane's channel: add the published partials (finisher), then either scale and
+      // hand fp16 rows of D to TMA, or publish the int32 partial.
       auto process = [&](uint32_t(&r)[16], int mb) {
         if (others > 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] += (uint32_t)pre[i];
           if (mb + mstep < rows) fetch_partials(mb + mstep, pre);
         }
-        if (!n_ok) return;
-        const bool full16 = mb + 16 <= rows;
         if (finish) {
-          __half* __restrict__ dp = dcol + (size_t)(m0 + mb) * ldn;
+          uint8_t* buf = stg + (sbuf & 1) * kStageD;
+          ++sbuf;
+          if (issuer) bulk_wait_group_read<1>();  // the store that last used this buffer has read it
+          named_bar_sync(grp_bar, 128);
+          __half* sp = reinterpret_cast<__half*>(buf) + 32 * q + lane;
           const float4* s4 = reinterpret_cast<const float4*>(s1_sm + mb);
-          if (full16) {  // branch-free fast path
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 sv = s4[g4];
-              const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 sv = s4[g4];
+            const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int i = 4 * g4 + j;
-                dp[(size_t)i * ldn] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]);
-              }
+            for (int j = 0; j < 4; ++j) {
+              const int i = 4 * g4 + j;
+              sp[i * kTileN] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]);
             }
-          } else {  // ragged last chunk: same arithmetic, only the store is predicated
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              const float4 sv = s4[g4];
-              const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int i = 4 * g4 + j;
-                const __half h = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]);
-                if (mb + i < rows) dp[(size_t)i * ldn] = h;
-              }
-            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
+          named_bar_sync(grp_bar, 128);
+          if (issuer) {
+            tma_store_2d(&tmap_d, smem_u32(buf), nt * kTileN, m0 + mb);
+            bulk_commit_group();
           }
         } else {
-          int* __restrict__ slot = ccol + (size_t)(ticket * m_pad + m0 + mb) * ldn;
-          if (full16) {
+          int* __restrict__ dst = cbase + (size_t)ticket * ticket_stride + (size_t)mb * kTileN;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) slot[(size_t)i * ldn] = (int)r[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (mb + i < rows) slot[(size_t)i * ldn] = (int)r[i];
-          }
+          for (int i = 0; i < 16; ++i) dst[i * kTileN] = (int)r[i];
         }
       };
       // Software-pipelined drain: the TMEM load of the next chunk is in flight while this one is converted and
-      // stored (a tcgen05.ld round trip is ~230 cycles with all epilogue warps active; TMEM reads run at 64 B/clk).
+      // stored (TMEM reads run at 64 B/clk per SM: 2048 cycles for a 128 x 256 accumulator).
       {
         uint32_t ra[16], rb[16];
         int mb = 16 * eh;
@@ -569,6 +562,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       if (epi_tid == 0) QQQ_TR(11, seg);
     }
+    if (issuer) bulk_wait_group_read<0>();  // the staging tiles must outlive the TMA stores that read them
   }
 
   tc_fence_before();
@@ -580,11 +574,12 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 }  // namespace
 
 size_t gemm_smem_bytes(const GemmParams& p) {
-  return 1024 + (size_t)p.stages_t * p.ksub * p.n_tok * 128 + (size_t)p.stages_w * p.ksub * (kStageB + kStageS) +
+  return 1024 + kEpiStageBytes + (size_t)p.stages_t * p.ksub * p.n_tok * 128 + (size_t)p.stages_w * p.ksub * (kStageB + kStageS) +
          8 * (2 * p.stages_w + 2 * p.stages_t + 2 * kMaxASlots + 4) + 16 + 4 * kMaxTok;
 }
 
-cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
+                        const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
   static bool attr_set[2][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
@@ -604,7 +599,7 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, co
   attr[0].val.programmaticStreamSerializationAllowed = 1;           // with the tail of the preceding kernel
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, p);
+  return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, tmap_d, p);
 }
 
 #ifdef QQQ_TRACE

@@ -120,15 +120,13 @@ def test_errors_match_reference_conditions():
         qqq_b200.qqq_gemm(t["A8"], t["B"], C, D, t["s1"], t["s2"], t["s3"], ws, 96, 128, -1, 16)
 
 
-@pytest.mark.parametrize("M,gs", [(1, -1), (16, 128), (128, -1), (1024, 128), (4096, -1)])
-def test_full_size_sweep_shape_vs_int_mm(M, gs):
-    """BASELINE sweep shape (K=8192, N=21760): too big for the numpy oracle in seconds, so check against an
-    independent exact path on the GPU: torch._int_mm on oracle-decoded int8 weights (size-independent property:
-    the accumulator is an exact integer), then the oracle's epilogue formula in torch fp32."""
-    K, N = 8192, 21760
+def check_vs_int_mm(M, K, N, gs):
+    """Shapes too big for the numpy oracle in seconds are checked against an independent exact path on the GPU:
+    torch._int_mm on oracle-decoded int8 weights (size-independent property: the accumulator is an exact integer),
+    then the oracle's epilogue formula in torch fp32."""
     dev = "cuda:0"
     g = torch.Generator(device="cpu").manual_seed(M + 17)
-    rng = np.random.default_rng(M)
+    rng = np.random.default_rng(M + K + N)
     per_group = gs != -1
     w = rng.integers(0, 16, size=(K, N)) if per_group else rng.integers(-8, 8, size=(K, N))
     B = O.pack_B(w, per_group)
@@ -152,3 +150,26 @@ def test_full_size_sweep_shape_vs_int_mm(M, gs):
     ref = ((acc.float() * torch.from_numpy(s2_nat).to(dev)[None, :]) * s1.to(dev)).half().cpu().numpy()
     assert np.array_equal(bits(D), bits(ref))
     assert int(ws.abs().sum()) == 0
+
+
+@pytest.mark.parametrize("M,gs", [(1, -1), (16, 128), (128, -1), (1024, 128), (4096, -1)])
+def test_full_size_sweep_shape_vs_int_mm(M, gs):
+    """BASELINE configs[4]: the sweep shape K=8192, N=21760 at every M of the sweep."""
+    check_vs_int_mm(M, 8192, 21760, gs)
+
+
+MODEL_SHAPES = [
+    # BASELINE configs[1]: Llama-2-7B prefill M=1024, per-channel
+    (1024, 4096, 4096, -1), (1024, 4096, 11008, -1), (1024, 11008, 4096, -1),
+    # configs[2]: Llama-3-8B decode batch 32, g128 (q/o, k/v, gate/up, down)
+    (32, 4096, 4096, 128), (32, 4096, 1024, 128), (32, 4096, 14336, 128), (32, 14336, 4096, 128),
+    # configs[3]: Llama-2-70B per-rank shards at tensor-parallel 8, per-channel (q, k/v, o, gate/up, down)
+    (1024, 8192, 1024, -1), (1024, 8192, 128, -1), (1024, 1024, 8192, -1), (1024, 8192, 3584, -1),
+    (1024, 3584, 8192, -1),
+]
+
+
+@pytest.mark.parametrize("M,K,N,gs", MODEL_SHAPES)
+def test_model_config_shapes_vs_int_mm(M, K, N, gs):
+    """Every distinct Linear shape of BASELINE configs[1]-[3] at the configured batch."""
+    check_vs_int_mm(M, K, N, gs)

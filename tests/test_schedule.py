@@ -68,13 +68,15 @@ def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
     # CTAs beyond the grid must have no work
     assert segments(p, p["grid"]) == []
     # split tiles: the kernel's contributor count formula, scratch capacity and lock words
-    slot_rows = p["m_tiles"] * p["n_tok"]
+    # C (64*max_par rows of N int32) holds compact [n_tok][128] partial tiles, block = ticket * a_tiles + tile
+    tile_ints = p["n_tok"] * 128
     for t, ctas in contributors.items():
         if len(ctas) > 1:
             assert t < p["a_tiles"]
             parts = (t * KU + KU - 1) // p["a_upc"] - (t * KU) // p["a_upc"] + 1
             assert parts == len(ctas)
-            assert (parts - 1) * slot_rows <= 64 * 16, "split tile needs more rows than C has"
+            last_block = (parts - 2) * p["a_tiles"] + t  # highest block index a contributor of this tile writes
+            assert (last_block + 1) * tile_ints <= 64 * 16 * N, "partial tiles do not fit C"
     if any(len(c) > 1 for c in contributors.values()):
         assert tiles <= (N // 128) * 16, "not enough lock words in workspace"
 
