@@ -21,6 +21,12 @@ __device__ __forceinline__ uint32_t op(uint32_t x, uint32_t a, uint32_t b) {
   if (OP == 7) asm volatile("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(a), "r"(b));              // IMAD
   if (OP == 8) asm volatile("shr.u32 %0, %1, 8;" : "=r"(d) : "r"(x));                                      // SHF
   if (OP == 9) asm volatile("add.f32 %0, %1, 0fCB000008;" : "=r"(d) : "r"(x));                            // FADD imm
+  if (OP == 10) asm volatile("cvt.rn.f32.s32 %0, %1;" : "=r"(d) : "r"(x));                                 // I2FP.F32.S32
+  if (OP == 11) { unsigned short h; asm volatile("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "r"(x)); d = h; }   // F2FP (one value)
+  if (OP == 12) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "r"(x), "r"(a));                   // F2FP.PACK_AB
+  if (OP == 13) asm volatile("cvt.rni.s32.f32 %0, %1;" : "=r"(d) : "r"(x));                                // F2I
+  if (OP == 14) { unsigned short lo16, hi16; asm volatile("mov.b32 {%0,%1}, %2;" : "=h"(lo16), "=h"(hi16) : "r"(x));
+                  asm volatile("cvt.f32.f16 %0, %1;" : "=r"(d) : "h"(lo16)); }                              // HADD2.F32 (half -> float)
   return d;
 }
 
@@ -77,5 +83,10 @@ int main() {
   run<7>("IMAD");
   run<8>("SHF");
   run<9>("FADD r,imm");
+  run<10>("I2FP.F32.S32");
+  run<11>("F2FP f16<-f32");
+  run<12>("F2FP.PACK_AB");
+  run<13>("F2I.S32.F32");
+  run<14>("cvt f32<-f16");
   return 0;
 }

@@ -10,6 +10,8 @@
 // HBM-bound: reads 2*M*K bytes, writes M*K + 4*M.  One 256-thread CTA per token row; the row stays in registers
 // between the max pass and the quantise pass (NCH 16-byte chunks per thread, NCH chosen from K so that the
 // register footprint — and with it the number of resident CTAs per SM — matches the row length).
+#include <type_traits>
+
 #include "qqq_common.cuh"
 
 namespace qqq {
@@ -18,19 +20,34 @@ constexpr int kQuantThreads = 256;
 
 __device__ __forceinline__ uint32_t habs2_u32(uint32_t v) { return v & 0x7FFF7FFFu; }
 
-__device__ __forceinline__ uint32_t quant4(uint32_t lo, uint32_t hi, float s) {
-  // lo, hi: two half2 (4 consecutive halves) -> 4 int8 packed little-endian
+// 4 consecutive halves -> 4 int8 packed little-endian:  int8(clamp(rint(x / s), -128, 127)).
+// FAST: s is finite and > 0.  The IEEE quotient RN(x/s) is then obtained without a division per element:
+// r = RN(1/s) once per row, q0 = RN(x*r), q = fma(fma(-s, q0, x), r, q0).  For every finite fp16 x and every positive
+// finite fp16-valued s this equals RN(x/s) bit for bit except for the sign of a zero result (checked exhaustively,
+// oracle/div_identity.c / tests/test_act_quant_identity.py), so the int8 result is identical.  Otherwise (all-zero
+// row: s = 0; inf/NaN in the row) the true division is used: x/0 = +-inf saturates, 0/0 = NaN converts to 0 (the
+// reference's float->int8 cast of NaN is undefined; CUDA's cvt gives 0).
+// cvt.rni (round-half-even, like torch.round) + cvt.pack.sat replace round/clamp/cast.
+template <bool FAST>
+__device__ __forceinline__ uint32_t quant4(uint32_t lo, uint32_t hi, float s, float r) {
   const __half2 a = *reinterpret_cast<const __half2*>(&lo);
   const __half2 b = *reinterpret_cast<const __half2*>(&hi);
-  float f[4] = {__low2float(a), __high2float(a), __low2float(b), __high2float(b)};
-  uint32_t out = 0;
+  const float f[4] = {__low2float(a), __high2float(a), __low2float(b), __high2float(b)};
+  int qi[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float q = rintf(__fdiv_rn(f[i], s));
-    // NaN (all-zero row: 0/0) -> 0: the reference's float->int8 cast of NaN is undefined; CUDA's cvt gives 0
-    int qi = (q == q) ? __float2int_rn(fminf(fmaxf(q, -128.f), 127.f)) : 0;
-    out |= (uint32_t)(qi & 0xFF) << (8 * i);
+    float q;
+    if (FAST) {
+      const float q0 = __fmul_rn(f[i], r);
+      q = __fmaf_rn(__fmaf_rn(-s, q0, f[i]), r, q0);
+    } else {
+      q = __fdiv_rn(f[i], s);
+    }
+    qi[i] = __float2int_rn(q);  // NaN -> 0, +-inf -> INT_MAX / INT_MIN
   }
+  uint32_t t, out;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(qi[3]), "r"(qi[2]), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(qi[1]), "r"(qi[0]), "r"(t));
   return out;
 }
 
@@ -40,8 +57,10 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
 }
 
 // NCH > 0: the row has at most NCH*256 chunks and lives in registers.  NCH == 0: any K, second pass re-reads x.
+// Rows up to 4096 halves (NCH <= 2) are held to 32 registers so that 8 CTAs fit an SM: 1184 rows per wave, i.e. a
+// 1024-token prefill is one wave instead of one full wave plus a 15 % tail.
 template <int NCH>
-__global__ void __launch_bounds__(kQuantThreads)
+__global__ void __launch_bounds__(kQuantThreads, (NCH >= 1 && NCH <= 2) ? 8 : 1)
 act_quant_kernel(const uint4* __restrict__ x, uint2* __restrict__ q, float* __restrict__ s1, int K8 /* K/8 */,
                  int ldx8 /* row stride of x in 16-byte units */) {
   grid_launch_dependents();  // the GEMM that consumes q/s1 may start its prologue and weight prefetch right away
@@ -88,18 +107,28 @@ act_quant_kernel(const uint4* __restrict__ x, uint2* __restrict__ q, float* __re
   const float inv127 = (float)(1.0 / 127.0);
   const float s = __half2float(__float2half_rn(__fmul_rn(__half2float(t), inv127)));
   if (threadIdx.x == 0) s1[row] = s;
-  if (NCH > 0) {
+  const bool fast = s > 0.f && s < __int_as_float(0x7F800000);  // uniform over the CTA
+  const float r = __frcp_rn(s);
+  auto quant_row = [&](auto fast_tag) {
+    constexpr bool F = decltype(fast_tag)::value;
+    if (NCH > 0) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      const int i = threadIdx.x + j * kQuantThreads;
-      if (i < K8) qr[i] = make_uint2(quant4(cache[j].x, cache[j].y, s), quant4(cache[j].z, cache[j].w, s));
+      for (int j = 0; j < NC; ++j) {
+        const int i = threadIdx.x + j * kQuantThreads;
+        if (i < K8)
+          qr[i] = make_uint2(quant4<F>(cache[j].x, cache[j].y, s, r), quant4<F>(cache[j].z, cache[j].w, s, r));
+      }
+    } else {
+      for (int i = threadIdx.x; i < K8; i += kQuantThreads) {
+        const uint4 v = __ldg(xr + i);
+        qr[i] = make_uint2(quant4<F>(v.x, v.y, s, r), quant4<F>(v.z, v.w, s, r));
+      }
     }
-  } else {
-    for (int i = threadIdx.x; i < K8; i += kQuantThreads) {
-      const uint4 v = __ldg(xr + i);
-      qr[i] = make_uint2(quant4(v.x, v.y, s), quant4(v.z, v.w, s));
-    }
-  }
+  };
+  if (fast)
+    quant_row(std::true_type{});
+  else
+    quant_row(std::false_type{});
 }
 
 template <int NCH>

@@ -216,44 +216,55 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     set_err("problem too large");
     return QQQ_ERR_PROB_SHAPE;
   }
+  // Unpack groups.  Decode-size tiles: 3 groups + 4 epilogue warps; from 128 tokens up the accumulator drain is the
+  // exposed part: 2 groups + 8 epilogue warps (measured for both modes: the per-group rescale is bound by the issue
+  // rate of the sub-partition, which a third warp on the same sub-partition cannot widen).
+  static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
+  const int g_auto = p.n_tok <= 64 ? 3 : 2;
+  (void)grouped;
+  p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
+  // Weight-ring depth must be a multiple of `period`.  Sub-block i = ksub*unit + sub is unpacked by group i % G,
+  // and a group only waits on the full-barrier of the stages it unpacks from.  mbarrier waits are by phase PARITY:
+  // a group that waits for unit w on a stage whose previous occupant (unit w - depth) it never waited on can find
+  // that barrier still one phase behind (previous data not landed yet) and would then pass on the stale parity.
+  // With depth % period == 0 every stage is always consumed by the same groups, in order, so each wait follows the
+  // wait on the previous occupant.  (ksub >= G: every group touches every unit, period 1.)
+  const int G = p.unpack_groups;
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  const int period = p.ksub >= G ? 1 : G / gcd(p.ksub, G);
   // smem rings.  Depth = latency x consumption rate: when one token tile covers M the weights stream from DRAM
   // (long latency, ~160 KB in flight); with several token tiles they mostly hit L2 (~64 KB).  The token ring
   // (L2-resident data) takes the rest, at least 3 and at most 6 stages.
   const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
   const int budget =
       kMaxSmemBytes - 1024 - kEpiStageBytes - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
-  const int target_w = p.m_tiles == 1 ? 163840 : 65536;
-  int nsw = (target_w + stage_w - 1) / stage_w;
-  nsw = nsw < 3 ? 3 : (nsw > kMaxStages ? kMaxStages : nsw);
-  int nst = 0;
+  const int max_w = kMaxStages / period * period;
+  auto round_w = [&](int n) { n = n > max_w ? max_w : n; return n / period * period; };
+  int nsw = 0, nst = 0;
   if (p.m_tiles > 1) {  // tensor-bound regime: the token ring comes first (~160 KB, (L2 latency + 512) / stages <= 512)
     nst = (163840 + stage_t - 1) / stage_t;
     nst = nst < 3 ? 3 : (nst > 6 ? 6 : nst);
-    nsw = (budget - nst * stage_t) / stage_w;
-    if (nsw > kMaxStages) nsw = kMaxStages;
-  }
-  if (p.m_tiles == 1 || nsw < 4) {
-    if (nsw < 3) nsw = 3;
-    for (; nsw >= 2; --nsw) {
+    if (env_nst >= 2 && env_nst <= kMaxStages) nst = env_nst;
+    for (; nst >= 2; --nst) {
+      nsw = round_w((budget - nst * stage_t) / stage_w);
+      if (nsw >= 4 || (nst <= 3 && nsw >= 2)) break;
+    }
+  } else {
+    nsw = round_w((163840 + stage_w - 1) / stage_w + period - 1);
+    if (nsw < period) nsw = period;
+    for (; nsw >= period && nsw >= 2; nsw -= period) {
       nst = (budget - nsw * stage_w) / stage_t;
       if (nst >= 3) break;
     }
+    if (nst > 6) nst = 6;
+    if (env_nst >= 2 && env_nst <= kMaxStages && nsw * stage_w + env_nst * stage_t <= budget) nst = env_nst;
   }
-  if (nst > 6) nst = 6;
-  if (env_nst >= 2 && env_nst <= kMaxStages && nsw * stage_w + env_nst * stage_t <= budget) nst = env_nst;
-  if (nst < 2 || nsw < 2) {
+  if (nst < 2 || nsw < 2 || nsw % period != 0 || nsw * stage_w + nst * stage_t > budget) {
     set_err("internal: no room for the smem rings (n_tok=%d ksub=%d)", p.n_tok, p.ksub);
     return QQQ_ERR_KERN_SHAPE;
   }
   p.stages_t = nst;
-  static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
-  // decode-size tiles: 3 unpack groups + 4 epilogue warps; from 128 tokens up the accumulator drain is the exposed
-  // part: 2 unpack groups + 8 epilogue warps (measured for both modes: the per-group rescale is bound by the fp16
-  // pipe of the sub-partition, which a third warp on the same sub-partition cannot widen).
-  const int g_auto = p.n_tok <= 64 ? 3 : 2;
-  (void)grouped;
-  p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
-  p.stages_w = nsw > kMaxStages ? kMaxStages : nsw;
+  p.stages_w = nsw;
 
   int grid = sm_count;
   if ((long long)grid > units) grid = (int)units;
@@ -393,6 +404,8 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   // weights are streamed once when a single token tile covers M; tokens are re-read by every CTA
   p.hint_b = p.m_tiles == 1 ? kEvictFirst : kEvictNormal;
   p.hint_a = kEvictLast;
+  static const int env_hints = getenv("QQQ_B200_HINTS") ? atoi(getenv("QQQ_B200_HINTS")) : 1;
+  if (env_hints == 0) p.hint_a = p.hint_b = kEvictNormal;  // experiments
 
   CUtensorMap tmap_a, tmap_b, tmap_d;
   if (!encode_2d(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, A, (uint64_t)K, (uint64_t)M, (uint64_t)K, kBlockK,

@@ -150,8 +150,12 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int NA = min(kMaxASlots, (512 - tmem_a0) / (32 * KSUB));
   const int tok_bytes = p.n_tok * 128;      // one sub-block of tokens
   const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
+#ifndef QQQ_STAGE_AT_END
   uint8_t* sStage = smem;                   // epilogue staging: 2 groups x 2 tiles of [16][128] fp16
   uint8_t* sT = sStage + kEpiStageBytes;
+#else
+  uint8_t* sT = smem;
+#endif
   uint8_t* sW = sT + NST * stage_t;
   uint8_t* sS = sW + NSW * stage_w;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSW * stage_s);
@@ -165,6 +169,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t bar_dempty = bar_dfull + 8 * 2;
   uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 2 * NSW + 2 * NST + 2 * kMaxASlots + 4);  // [0] tmem base, [1] flag
   float* s1_sm = reinterpret_cast<float*>(misc + 4);                                            // [kMaxTok]
+#ifdef QQQ_STAGE_AT_END
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s1_sm + kMaxTok) + 127) & ~(uintptr_t)127);
+#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.unpack_groups;                 // 2 or 3 groups of unpack warps (host policy in qqq_c_api.cu)
@@ -182,7 +189,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
+#ifndef QQQ_NO_DPREFETCH
       tma_prefetch_desc(&tmap_d);
+#endif
     }
     for (int i = lane; i < NSW; i += 32) {
       mbar_init(bar_fullw + 8 * i, 1);
@@ -232,7 +241,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     return true;
   };
+#ifndef QQQ_NO_WPREFETCH
   if (warp == 0) {
+#else
+  if (false) {
+#endif
     while (w_count < NSW && w_next()) {
       if (elect_one()) issue_weights(w_st.idx, w_tile / p.m_tiles, w_kb);
       __syncwarp();
@@ -494,6 +507,17 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           for (int i = 0; i < 16; ++i) r[i] += (uint32_t)pre[i];
           if (mb + mstep < rows) fetch_partials(mb + mstep, pre);
         }
+#ifdef QQQ_DIRECT_STORE  // debugging aid: per-lane global stores instead of the smem tile + TMA store
+        if (finish) {
+          if (n_ok) {
+            __half* dp = p.D + (size_t)(m0 + mb) * p.N + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (mb + i < rows)
+                dp[(size_t)i * p.N] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * s1_sm[mb + i]);
+          }
+        } else
+#endif
         if (finish) {
           uint8_t* buf = stg + (sbuf & 1) * kStageD;
           ++sbuf;
@@ -528,6 +552,14 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       {
         uint32_t ra[16], rb[16];
         int mb = 16 * eh;
+#ifdef QQQ_NO_LD_PIPELINE  // debugging aid: one TMEM load in flight at a time
+        for (; mb < rows; mb += mstep) {
+          tmem_ld_32x32b_x16(tmem_d + mb, ra);
+          tmem_wait_ld();
+          process(ra, mb);
+        }
+        (void)rb;
+#endif
         if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
         while (mb < rows) {
           tmem_wait_ld();

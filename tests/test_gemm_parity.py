@@ -173,3 +173,39 @@ MODEL_SHAPES = [
 def test_model_config_shapes_vs_int_mm(M, K, N, gs):
     """Every distinct Linear shape of BASELINE configs[1]-[3] at the configured batch."""
     check_vs_int_mm(M, K, N, gs)
+
+
+def test_repeated_launches_behind_a_dirty_l2():
+    """Regression: with an L2 full of dirty lines (a large fill just ran) weight tiles land late and out of order.
+    A weight-ring depth that let a stage alternate between unpack groups made a group pass its full-barrier on a
+    stale phase parity (launch failure / wrong sums).  Every launch must reproduce the first result bit for bit,
+    and the first result is checked against the exact integer path."""
+    import qqq_b200
+
+    dev = "cuda:0"
+    M, K, N = 2048, 8192, 21760
+    g = torch.Generator(device=dev).manual_seed(3)
+    B = torch.randint(-2**31, 2**31 - 1, (K // 16, 2 * N), dtype=torch.int32, device=dev, generator=g)
+    A = torch.randint(-128, 128, (M, K), dtype=torch.int8, device=dev, generator=g)
+    s1 = torch.rand(M, 1, device=dev, generator=g) * 1e-2 + 1e-3
+    s2_nat = torch.rand(N, device=dev, generator=g) * 1e-3 + 5e-4
+    s2 = torch.from_numpy(O.permute_s_channel(s2_nat.cpu().numpy())).to(dev)
+    s3 = torch.zeros(0, dtype=torch.float16, device=dev)
+    C = torch.zeros(16 * 64, N, dtype=torch.int32, device=dev)
+    ws = torch.zeros(N // 128 * 16, dtype=torch.int32, device=dev)
+    junk = torch.empty(96 * 1024 * 1024, dtype=torch.float16, device=dev)  # 192 MB > L2
+    first = None
+    for it in range(16):
+        junk.fill_(float(it))
+        D = torch.full((M, N), float("nan"), dtype=torch.float16, device=dev)
+        qqq_b200.qqq_gemm(A, B, C, D, s1, s2, s3, ws, -1, -1, -1, 16)
+        torch.cuda.synchronize()
+        if first is None:
+            first = D
+        else:
+            assert torch.equal(D.view(torch.int16), first.view(torch.int16)), f"launch {it} differs from launch 0"
+    W8 = torch.from_numpy(O.w8_per_channel(O.unpack_B(B.cpu().numpy(), False) & 0xF).astype(np.int8)).to(dev)
+    acc = torch._int_mm(A, W8)
+    ref = ((acc.float() * s2_nat[None, :]) * s1).half()
+    assert torch.equal(first.view(torch.int16), ref.view(torch.int16))
+    assert int(ws.abs().sum()) == 0

@@ -3,6 +3,7 @@ shapes and SM counts, replay the kernel's segment walk (Sched in qqq_gemm_sm100.
 (tile, k-unit) is produced exactly once, that split tiles fit the caller's scratch (C rows, lock words) and that
 the launch fits the SM's shared memory."""
 import ctypes
+import math
 
 import pytest
 
@@ -55,6 +56,15 @@ def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
     assert p["ksub"] in (1, 2, 4) and KU == -(-p["k_blocks"] // p["ksub"])
     assert p["smem_bytes"] <= 232448 and p["stages_w"] >= 2 and p["stages_t"] >= 2
     assert p["unpack_groups"] in (2, 3)
+    # a weight stage must always be consumed by the same unpack groups (mbarrier waits are by phase parity):
+    # sub-block i = ksub*unit + sub belongs to group i % G, so the ring depth has to be a multiple of the period of
+    # that ownership pattern in units
+    G, ks = p["unpack_groups"], p["ksub"]
+    period = 1 if ks >= G else G // math.gcd(ks, G)
+    assert p["stages_w"] % period == 0, f"weight ring depth {p['stages_w']} not a multiple of {period}"
+    for g in range(G):
+        owned = lambda u: any((ks * u + sub) % G == g for sub in range(ks))
+        assert all(owned(u) == owned(u + p["stages_w"]) for u in range(64))
     seen = {}
     contributors = {}
     for cta in range(p["grid"]):
