@@ -51,6 +51,11 @@ if len(E13) and len(E13) == len(E14):
     stats("epilogue warp 0: chunk convert+store (TR14-TR13)", E14 - E13)
     if len(E13) > 1:
         stats("epilogue warp 0: wait for next chunk's tcgen05.ld (TR13[i+1]-TR14[i])", E13[1:] - E14[:-1])
+E9, E15 = rel(9), rel(15)
+if len(E9) and len(E9) == len(E13) and len(E15) == len(E13):
+    stats("epilogue warp 0: next LDTM issue + convert + 16 STS (TR9-TR13)", E9 - E13)
+    stats("epilogue warp 0: __syncwarp (TR15-TR9)", E15 - E9)
+    stats("epilogue warp 0: 2 LDS.128 + 2 STG.128 + __syncwarp (TR14-TR15)", E14 - E15)
 idx = np.nonzero(t[2])[0]
 u2 = t[2, idx].astype(np.int64) - t0; u3 = t[3, idx].astype(np.int64) - t0; u10 = t[10, idx].astype(np.int64) - t0; u4 = t[4, idx].astype(np.int64) - t0
 stats("unpack(q0 warps): LDS issue + wait aempty (TR3-TR2)", u3 - u2)

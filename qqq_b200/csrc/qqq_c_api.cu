@@ -275,7 +275,8 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   const long long whole_per_cta = tiles / grid;
   const long long rem = tiles - whole_per_cta * grid;
   long long a_tiles = 0, a_upc = 1;
-  if (rem > 0 && has_scratch && tiles <= (long long)(N / 128) * max_par && (double)rem / grid < 0.92) {
+  static const int env_split = getenv("QQQ_B200_SPLIT") ? atoi(getenv("QQQ_B200_SPLIT")) : -1;  // experiments
+  if (rem > 0 && has_scratch && tiles <= (long long)(N / 128) * max_par && env_split != 0) {
     const long long tile_ints = (long long)p.n_tok * kTileN;  // one partial tile
     const long long c_ints = 64ll * max_par * N;              // capacity of C
     auto parts_max = [&](long long upc) { return (upc % p.k_units == 0) ? 1ll : (p.k_units - 1) / upc + 2; };
@@ -290,8 +291,24 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
       a_tiles = rem;
       a_upc = upc_rem;
     } else if ((parts_max(upc_all) - 1) * tiles * tile_ints <= c_ints) {
-      a_tiles = tiles;
-      a_upc = upc_all;
+      // Stream-K over all tiles balances the SMs but costs every CTA one more accumulator drain (its partial of a
+      // straddled tile), which is exposed when the accumulator is single-buffered.  Cycle model from the in-kernel
+      // timelines (profiles/): a k-block costs 4 MMAs of max(48 issue, n_tok/2 pipe) cycles + ~48 of hand-off, and
+      // not less than ~420 when the weights stream from DRAM (one token tile); a drain costs ~730 cycles per
+      // 16-token chunk and epilogue warp + ~1400 fixed.
+      const double c_kb = 4.0 * (p.n_tok / 2 > 48 ? p.n_tok / 2 : 48) + 48.0;
+      const double t_u = p.ksub * (p.m_tiles == 1 && c_kb < 420.0 ? 420.0 : c_kb);
+      const int n_epi = kWarps - kUnpackWarp0 - 4 * p.unpack_groups;
+      const double t_d = 730.0 * ((p.n_tok / 16 + n_epi / 4 - 1) / (n_epi / 4)) + 1400.0;
+      const bool dbuf = p.n_tok <= 192;  // double-buffered accumulators: only the last drain of a CTA is exposed
+      const long long waves = (tiles + grid - 1) / grid;
+      const double cost_whole = (double)waves * p.k_units * t_u + (dbuf ? 1.0 : (double)waves) * t_d;
+      const long long segs = (upc_all + p.k_units - 1) / p.k_units + 1;
+      const double cost_split = (double)upc_all * t_u + (dbuf ? 1.0 : (double)segs) * t_d;
+      if (env_split == 1 || cost_split < cost_whole) {
+        a_tiles = tiles;
+        a_upc = upc_all;
+      }
     }
   }
   p.a_tiles = (int)a_tiles;
@@ -407,7 +424,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   static const int env_hints = getenv("QQQ_B200_HINTS") ? atoi(getenv("QQQ_B200_HINTS")) : 1;
   if (env_hints == 0) p.hint_a = p.hint_b = kEvictNormal;  // experiments
 
-  CUtensorMap tmap_a, tmap_b, tmap_d;
+  CUtensorMap tmap_a, tmap_b;
   if (!encode_2d(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, A, (uint64_t)K, (uint64_t)M, (uint64_t)K, kBlockK,
                  (uint32_t)p.n_tok, CU_TENSOR_MAP_SWIZZLE_128B))
     return QQQ_ERR_CUDA;
@@ -415,12 +432,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
                  2 * kTileN, 8 * p.ksub, CU_TENSOR_MAP_SWIZZLE_NONE))
     return QQQ_ERR_CUDA;
 
-  // D as a TMA-store target: [M rows][N fp16], boxes of 16 tokens x 128 channels (clipped at M and N)
-  if (!encode_2d(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, D, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, kTileN, 16,
-                 CU_TENSOR_MAP_SWIZZLE_NONE))
-    return QQQ_ERR_CUDA;
-
-  cudaError_t e = launch_gemm(tmap_a, tmap_b, tmap_d, p, grouped, grid, dev, stream, use_pdl());
+  cudaError_t e = launch_gemm(tmap_a, tmap_b, p, grouped, grid, dev, stream, use_pdl());
   if (e != cudaSuccess) {
     set_err("kernel launch failed: %s", cudaGetErrorString(e));
     return QQQ_ERR_CUDA;

@@ -32,14 +32,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) expires: with a long hint a
+// waiting warp issues (almost) no polling instructions, which would otherwise compete for the issue slots of the
+// working warps of its SM sub-partition; the wake-up on completion is immediate either way.
+#ifndef QQQ_SUSPEND_HINT_NS
+#define QQQ_SUSPEND_HINT_NS 1000000
+#endif
+constexpr uint32_t kSuspendHintNs = QQQ_SUSPEND_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
@@ -175,18 +182,6 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
       "l"(gsrc), "r"(bytes), "r"(bar)
       : "memory");
-}
-// 2-D tile shared -> global through a tensor map (bulk async-group completion; out-of-bounds parts are clipped)
-__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
-               "r"(smem_src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// wait until at most N of this thread's bulk groups still have to READ their shared-memory source
-template <int N>
-__device__ __forceinline__ void bulk_wait_group_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 // L2 eviction-priority policies (createpolicy encodings used by CUTLASS' TMA::CacheHintSm90)
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;

@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t unpack_pg4(uint32_t w, uint32_t s2h) {
 template <bool GROUPED>
 __global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
+                const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -150,12 +150,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int NA = min(kMaxASlots, (512 - tmem_a0) / (32 * KSUB));
   const int tok_bytes = p.n_tok * 128;      // one sub-block of tokens
   const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
-#ifndef QQQ_STAGE_AT_END
-  uint8_t* sStage = smem;                   // epilogue staging: 2 groups x 2 tiles of [16][128] fp16
+  uint8_t* sStage = smem;                   // epilogue staging: one [16][32] fp16 tile per epilogue warp
   uint8_t* sT = sStage + kEpiStageBytes;
-#else
-  uint8_t* sT = smem;
-#endif
   uint8_t* sW = sT + NST * stage_t;
   uint8_t* sS = sW + NSW * stage_w;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSW * stage_s);
@@ -169,9 +165,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t bar_dempty = bar_dfull + 8 * 2;
   uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 2 * NSW + 2 * NST + 2 * kMaxASlots + 4);  // [0] tmem base, [1] flag
   float* s1_sm = reinterpret_cast<float*>(misc + 4);                                            // [kMaxTok]
-#ifdef QQQ_STAGE_AT_END
-  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s1_sm + kMaxTok) + 127) & ~(uintptr_t)127);
-#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.unpack_groups;                 // 2 or 3 groups of unpack warps (host policy in qqq_c_api.cu)
@@ -189,9 +182,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
-#ifndef QQQ_NO_DPREFETCH
-      tma_prefetch_desc(&tmap_d);
-#endif
     }
     for (int i = lane; i < NSW; i += 32) {
       mbar_init(bar_fullw + 8 * i, 1);
@@ -241,11 +231,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     return true;
   };
-#ifndef QQQ_NO_WPREFETCH
   if (warp == 0) {
-#else
-  if (false) {
-#endif
     while (w_count < NSW && w_next()) {
       if (elect_one()) issue_weights(w_st.idx, w_tile / p.m_tiles, w_kb);
       __syncwarp();
@@ -416,13 +402,14 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int epi_tid = threadIdx.x - epi_warp0 * 32;
     const int eh = (warp - epi_warp0) >> 2;  // which of the n_epi/4 warps of this quadrant: takes every (n_epi/4)-th chunk
     const int mstep = 16 * (n_epi >> 2);
-    // D leaves through shared memory: the 4 quadrant warps of a group transpose one 16-token chunk into a
-    // [16 tokens][128 channels] fp16 tile (row = 256 B) and one thread hands it to TMA (coalesced full-line writes;
-    // rows past M and channels past N are clipped by the tensor map).  Two tiles per group, alternating.
-    uint8_t* stg = sStage + eh * (2 * kStageD);
-    const uint32_t grp_bar = 2 + eh;             // named barrier of this group's 4 warps
-    const bool issuer = (q == 0) && (lane == 0); // bulk async-groups are per thread: always the same one
-    int sbuf = 0;
+    // D leaves through a warp-private shared-memory tile: the warp holds a chunk as [channel = lane][16 tokens]; it
+    // writes it as [16 tokens][32 channels] fp16 (row = 64 B, conflict-free), then every lane re-reads 16 B = 8
+    // channels of one token and stores them: 2 vector stores per lane and chunk (each instruction covers 8 token
+    // rows x 64 B) instead of 16 two-byte stores on a serial address chain.  (Measured alternatives, profiles/r01:
+    // a TMA store per 4-warp group or per warp, and half2 token-pair staging, were all slower: the drain is bound by
+    // the issue rate of the two epilogue warps of a sub-partition, ~730 cycles per 16-token chunk.)
+    unsigned short* stg = reinterpret_cast<unsigned short*>(sStage + (warp - epi_warp0) * kStageD);
+    const int st_tok = lane >> 2, st_part = lane & 3;  // this lane's token row (and +8) and 8-channel part of the tile
     const size_t tile_ints = (size_t)p.n_tok * kTileN;  // one partial tile in C
     grid_dependency_wait();  // s1 comes from the preceding kernel; D / C / lock words may still be in use by it
     int staged_mt = -1;
@@ -437,6 +424,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const uint32_t dph = (seg / ndbuf) & 1;
       const int n = nt * kTileN + 32 * q + lane;
       const bool n_ok = n < p.N;
+      const bool q_ok = nt * kTileN + 32 * q < p.N;  // warp-uniform
       const int m0 = mt * p.n_tok;
       const int rows = min(p.n_tok, p.M - m0);  // valid token rows of this tile
       const bool whole = (kb0 == 0 && kb1 == KU);
@@ -499,31 +487,16 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       };
       if (others > 0 && 16 * eh < rows) fetch_partials(16 * eh, pre);
 
-      // One 16-token chunk of this lane's channel: add the published partials (finisher), then either scale and
-      // hand fp16 rows of D to TMA, or publish the int32 partial.
+      // One 16-token chunk of this lane's channel: add the published partials (finisher), then either scale,
+      // transpose through the warp's tile and store fp16 rows of D, or publish the int32 partial.
       auto process = [&](uint32_t(&r)[16], int mb) {
         if (others > 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) r[i] += (uint32_t)pre[i];
           if (mb + mstep < rows) fetch_partials(mb + mstep, pre);
         }
-#ifdef QQQ_DIRECT_STORE  // debugging aid: per-lane global stores instead of the smem tile + TMA store
         if (finish) {
-          if (n_ok) {
-            __half* dp = p.D + (size_t)(m0 + mb) * p.N + n;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (mb + i < rows)
-                dp[(size_t)i * p.N] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * s1_sm[mb + i]);
-          }
-        } else
-#endif
-        if (finish) {
-          uint8_t* buf = stg + (sbuf & 1) * kStageD;
-          ++sbuf;
-          if (issuer) bulk_wait_group_read<1>();  // the store that last used this buffer has read it
-          named_bar_sync(grp_bar, 128);
-          __half* sp = reinterpret_cast<__half*>(buf) + 32 * q + lane;
+          unsigned short* sp = stg + lane;
           const float4* s4 = reinterpret_cast<const float4*>(s1_sm + mb);
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
@@ -532,15 +505,20 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int i = 4 * g4 + j;
-              sp[i * kTileN] = __float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]);
+              sp[i * 32] = __half_as_ushort(__float2half_rn((__int2float_rn((int)r[i]) * s2v) * sa[j]));
             }
           }
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
-          named_bar_sync(grp_bar, 128);
-          if (issuer) {
-            tma_store_2d(&tmap_d, smem_u32(buf), nt * kTileN, m0 + mb);
-            bulk_commit_group();
+          if (epi_tid == 0) QQQ_TR(9, echunk);
+          __syncwarp();
+          if (epi_tid == 0) QQQ_TR(15, echunk);
+          if (q_ok) {  // the whole 32-channel quadrant is inside N (N % 64 == 0) or outside
+            const uint4* rp = reinterpret_cast<const uint4*>(stg) + lane;  // row st_tok, part st_part
+            const uint4 v0 = rp[0], v1 = rp[32];                            // rows st_tok and st_tok + 8
+            __half* dp = p.D + (size_t)(m0 + mb + st_tok) * p.N + (nt * kTileN + 32 * q + 8 * st_part);
+            if (mb + st_tok < rows) *reinterpret_cast<uint4*>(dp) = v0;
+            if (mb + st_tok + 8 < rows) *reinterpret_cast<uint4*>(dp + (size_t)8 * p.N) = v1;
           }
+          __syncwarp();  // the tile is rewritten by the next chunk
         } else {
           int* __restrict__ dst = cbase + (size_t)ticket * ticket_stride + (size_t)mb * kTileN;
 #pragma unroll
@@ -552,14 +530,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       {
         uint32_t ra[16], rb[16];
         int mb = 16 * eh;
-#ifdef QQQ_NO_LD_PIPELINE  // debugging aid: one TMEM load in flight at a time
-        for (; mb < rows; mb += mstep) {
-          tmem_ld_32x32b_x16(tmem_d + mb, ra);
-          tmem_wait_ld();
-          process(ra, mb);
-        }
-        (void)rb;
-#endif
         if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
         while (mb < rows) {
           tmem_wait_ld();
@@ -594,7 +564,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       if (epi_tid == 0) QQQ_TR(11, seg);
     }
-    if (issuer) bulk_wait_group_read<0>();  // the staging tiles must outlive the TMA stores that read them
   }
 
   tc_fence_before();
@@ -610,8 +579,7 @@ size_t gemm_smem_bytes(const GemmParams& p) {
          8 * (2 * p.stages_w + 2 * p.stages_t + 2 * kMaxASlots + 4) + 16 + 4 * kMaxTok;
 }
 
-cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
-                        const GemmParams& p, bool grouped,
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
   static bool attr_set[2][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
@@ -631,7 +599,7 @@ cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, co
   attr[0].val.programmaticStreamSerializationAllowed = 1;           // with the tail of the preceding kernel
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, tmap_d, p);
+  return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, p);
 }
 
 #ifdef QQQ_TRACE

@@ -16,8 +16,8 @@ constexpr int kMaxASlots = 8;    // ring slots of 32*ksub columns each
 constexpr int kMaxStages = 16;
 constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
 constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
-constexpr int kStageD = 4096;          // one epilogue staging tile: 16 tokens x 128 channels fp16
-constexpr int kEpiStageBytes = 2 * 2 * kStageD;  // up to 2 epilogue groups x 2 alternating tiles
+constexpr int kStageD = 1024;          // one epilogue staging tile: 16 tokens x 32 channels fp16 (one warp's chunk)
+constexpr int kEpiStageBytes = 8 * kStageD;  // up to 8 epilogue warps
 // warp roles: 0 weights TMA, 1 MMA (+TMEM alloc), 2 tokens TMA, 3 idle, then 4*G unpack warps (G groups x 4 TMEM
 // lane quadrants) and the remaining 16-4G warps as epilogue (G = 2: 8 epilogue warps, G = 3: 4).  24 warps
 // (G up to 4) were measured and did not help: all warps of a TMEM quadrant share one SM sub-partition, so extra
@@ -50,7 +50,7 @@ struct GemmParams {
 };
 
 size_t gemm_smem_bytes(const GemmParams& p);
-cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const CUtensorMap& tmap_d,
-                        const GemmParams& p, bool grouped, int grid, int dev, cudaStream_t stream, bool pdl);
+cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
+                        int grid, int dev, cudaStream_t stream, bool pdl);
 
 }  // namespace qqq
