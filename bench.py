@@ -462,13 +462,13 @@ def main():
     int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
     achieved = flops_rank / (ms_gemm * 1e-3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01", "ncu", "traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01", "final", "ncu", "traffic.json")
     if world == 1 and os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full captures
         traffic = json.load(open(tpath)).get("llama2_7b_prefill_m1024", {}).get("avg_per_launch")
     roofline = dict(bound="tensor", kernel="qqq_gemm_kernel<per-channel> (tcgen05 kind::i8)", achieved=round(achieved, 1),
                     peak=round(int8_peak, 1), unit="TFLOP/s", frac=round(achieved / int8_peak, 4), traffic=traffic,
                     traffic_note="dram__bytes_read+write per launch, mean over the 7 GEMMs of a layer (ncu, "
-                                 "profiles/r01/ncu/traffic.json); below the algorithmic bytes because A8 and D stay in L2",
+                                 "profiles/r01/final/ncu/traffic.json); below the algorithmic bytes because A8 and D stay in L2",
                     peak_source=f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['source']}); int8 dense = 2x bf16 "
                                 "on sm_100a; UTCIMMA-only microbenchmark on this pool measured 4428 TOP/s burst "
                                 "(profiles/r01/probe_umma_i8.log)",
