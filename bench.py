@@ -390,7 +390,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
             os.environ["NCCL_DEBUG"] = "WARN"  # NCCL would print its version banner to stdout ahead of the JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
         barrier = lambda: dist.barrier()  # noqa: E731
