@@ -5,10 +5,10 @@ O=gpurun_out/$1; mkdir -p $O/ncu
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 timeout 900 python bench.py > $O/bench.json 2> $O/bench.err
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
+[ -z "$SKIP_REF" ] && timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"qqq_gemm_kernel|act_quant_kernel" --launch-skip 1344 -c 896 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 1 --no-sweep --no-cpu --no-merged > $O/bench_under_ncu.log 2>&1
 M="dram__bytes_read.sum,dram__bytes_write.sum"
-for cfg in "16 -1 8192 21760" "1024 -1 8192 21760" "16 128 8192 21760" "1024 128 8192 21760" "1024 -1 4096 4096" "1024 -1 4096 11008" "1024 -1 11008 4096"; do
+for cfg in ${NCU_CFGS:-"16 -1 8192 21760" "1024 -1 8192 21760" "16 128 8192 21760" "1024 128 8192 21760" "1024 -1 4096 4096" "1024 -1 4096 11008" "1024 -1 11008 4096"}; do
   set -- $cfg
   name=m$1_g$2_k$3_n$4
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:qqq_gemm_kernel --launch-skip 3 -c 1 -o $O/ncu/$name -f python probes/run_one.py $1 $2 5 $3 $4 > $O/ncu/$name.log 2>&1

@@ -210,7 +210,17 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   if (env_ksub == 1 || env_ksub == 2 || env_ksub == 4) p.ksub = env_ksub;
   while (p.ksub > 1 && p.k_blocks < p.ksub) p.ksub >>= 1;
   p.k_units = (p.k_blocks + p.ksub - 1) / p.ksub;
-  const long long tiles = (long long)p.m_tiles * p.n_tiles;
+  // CTA pairs (cluster of 2, cta_group::2, see qqq_gemm_sm100.cu): two CTAs share a token tile and each loads half of
+  // it.  Measured (profiles/r01/pair_mode.log): +7-9 % when every SM walks several 256-token tiles (M >= 1024 at
+  // N = 21760), neutral at ~2 tiles per SM, slower when there is at most one tile per SM or the tiles are small.
+  // QQQ_B200_PAIR=0/1 overrides the policy (1: wherever the shape allows it).
+  static const int env_pair = getenv("QQQ_B200_PAIR") ? atoi(getenv("QQQ_B200_PAIR")) : -1;
+  const bool pair_ok = p.n_tiles % 2 == 0 && p.n_tok % 32 == 0 && sm_count >= 2;
+  const bool pair_auto = p.n_tok == kMaxTok && p.m_tiles >= 2 && 2ll * p.m_tiles * p.n_tiles >= 5ll * sm_count;
+  p.pair = (pair_ok && (env_pair == 1 || (env_pair != 0 && pair_auto))) ? 1 : 0;
+  const int sched_cols = p.n_tiles >> p.pair;   // scheduled (super-)tiles per token tile
+  const int sched_ctas = sm_count >> p.pair;    // CTAs (pairs) the schedule is distributed over
+  const long long tiles = (long long)p.m_tiles * sched_cols;
   const long long units = tiles * p.k_units;
   if (units >= (1ll << 31)) {
     set_err("problem too large");
@@ -235,7 +245,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   // smem rings.  Depth = latency x consumption rate: when one token tile covers M the weights stream from DRAM
   // (long latency, ~160 KB in flight); with several token tiles they mostly hit L2 (~64 KB).  The token ring
   // (L2-resident data) takes the rest, at least 3 and at most 6 stages.
-  const int stage_t = p.ksub * p.n_tok * 128, stage_w = p.ksub * (kStageB + kStageS);
+  const int stage_t = p.ksub * (p.n_tok >> p.pair) * 128, stage_w = p.ksub * (kStageB + kStageS);
   const int budget =
       kMaxSmemBytes - 1024 - kEpiStageBytes - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
   const int max_w = kMaxStages / period * period;
@@ -266,7 +276,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   p.stages_t = nst;
   p.stages_w = nsw;
 
-  int grid = sm_count;
+  int grid = sched_ctas;
   if ((long long)grid > units) grid = (int)units;
   // Schedule.  Whole tiles go round the CTAs in waves; the remainder tiles that would leave SMs idle in a last
   // partial wave are instead cut along K over all CTAs (stream-K) when the caller's scratch allows it: C (64*max_par
@@ -276,8 +286,8 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   const long long rem = tiles - whole_per_cta * grid;
   long long a_tiles = 0, a_upc = 1;
   static const int env_split = getenv("QQQ_B200_SPLIT") ? atoi(getenv("QQQ_B200_SPLIT")) : -1;  // experiments
-  if (rem > 0 && has_scratch && tiles <= (long long)(N / 128) * max_par && env_split != 0) {
-    const long long tile_ints = (long long)p.n_tok * kTileN;  // one partial tile
+  if (rem > 0 && has_scratch && (tiles << p.pair) <= (long long)(N / 128) * max_par && env_split != 0) {
+    const long long tile_ints = ((long long)p.n_tok * kTileN) << p.pair;  // partial tile(s) of one scheduled tile
     const long long c_ints = 64ll * max_par * N;              // capacity of C
     auto parts_max = [&](long long upc) { return (upc % p.k_units == 0) ? 1ll : (p.k_units - 1) / upc + 2; };
     // (1) cut only the remainder tiles, over all CTAs, ahead of the whole tiles (fix-up hidden behind the rest)
@@ -323,7 +333,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   } else {
     grid = (int)((p.a_units + a_upc - 1) / a_upc);
   }
-  *grid_out = grid;
+  *grid_out = grid << p.pair;
   return QQQ_OK;
 }
 
@@ -331,21 +341,21 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
 
 extern "C" {
 
-int qqq_b200_version(void) { return 100; }
+int qqq_b200_version(void) { return 101; }
 const char* qqq_b200_last_error(void) { return g_err; }
 long long qqq_b200_launch_count(void) { return g_launches.load(); }
 
-int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_count, int max_par, int* out /* [16] */) {
+int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_count, int max_par, int* out /* [20] */) {
   qqq::GemmParams p;
   memset(&p, 0, sizeof(p));
   int grid = 0;
   if (prob_m <= 0 || prob_n <= 0 || prob_k <= 0 || sm_count <= 0 || out == nullptr) return QQQ_ERR_PROB_SHAPE;
   const int rc = plan_gemm(prob_m, prob_n, prob_k, groupsize == 128, sm_count, max_par, true, p, &grid);
   if (rc != QQQ_OK) return rc;
-  const int v[16] = {grid,      p.n_tok,   p.m_tiles, p.n_tiles,  p.k_blocks, p.ksub,    p.k_units,      p.a_tiles,
+  const int v[20] = {grid,      p.n_tok,   p.m_tiles, p.n_tiles,  p.k_blocks, p.ksub,    p.k_units,      p.a_tiles,
                      p.a_units, p.a_upc,   p.b_tiles, p.b_tpc,    p.stages_w, p.stages_t, p.unpack_groups,
-                     (int)qqq::gemm_smem_bytes(p)};
-  for (int i = 0; i < 16; ++i) out[i] = v[i];
+                     (int)qqq::gemm_smem_bytes(p), p.pair, 0, 0, 0};
+  for (int i = 0; i < 20; ++i) out[i] = v[i];
   return QQQ_OK;
 }
 
@@ -426,7 +436,7 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
 
   CUtensorMap tmap_a, tmap_b;
   if (!encode_2d(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, A, (uint64_t)K, (uint64_t)M, (uint64_t)K, kBlockK,
-                 (uint32_t)p.n_tok, CU_TENSOR_MAP_SWIZZLE_128B))
+                 (uint32_t)(p.n_tok >> p.pair), CU_TENSOR_MAP_SWIZZLE_128B))
     return QQQ_ERR_CUDA;
   if (!encode_2d(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_INT32, B, (uint64_t)2 * N, (uint64_t)(K / 16), (uint64_t)N * 8,
                  2 * kTileN, 8 * p.ksub, CU_TENSOR_MAP_SWIZZLE_NONE))

@@ -134,7 +134,7 @@ __device__ __forceinline__ uint32_t unpack_pg4(uint32_t w, uint32_t s2h) {
   return out;
 }
 
-template <bool GROUPED>
+template <bool GROUPED, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
@@ -148,7 +148,13 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int ndbuf = p.n_tok <= 192 ? 2 : 1;
   const int tmem_a0 = ndbuf * p.n_tok;
   const int NA = min(kMaxASlots, (512 - tmem_a0) / (32 * KSUB));
-  const int tok_bytes = p.n_tok * 128;      // one sub-block of tokens
+  // CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent 128-channel tiles of the same token tile
+  // and the same k-range; one MMA instruction of the leader (rank 0) drives both tensor cores (UMMA M = 256), every
+  // CTA loads only its half of the token tile (rows [rank*n_tok/2, ...)), halving the L2->SM token traffic per SM.
+  constexpr int PAIR = kPair ? 1 : 0;  // a template parameter: kernels with cta_group::2 instructions need a cluster launch
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tok_rows = PAIR ? p.n_tok / 2 : p.n_tok;  // token rows this CTA holds per sub-block
+  const int tok_bytes = tok_rows * 128;               // one sub-block of tokens in this CTA's shared memory
   const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
   uint8_t* sStage = smem;                   // epilogue staging: one [16][32] fp16 tile per epilogue warp
   uint8_t* sT = sStage + kEpiStageBytes;
@@ -172,7 +178,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int n_epi = kWarps - epi_warp0;          // 8 or 4 epilogue warps
   const int n_epi_thr = 32 * n_epi;
   const int KU = p.k_units;  // units per tile
-  const Sched sched(p, (int)blockIdx.x);
+  const Sched sched(p, (int)blockIdx.x >> PAIR);  // the schedule is over (super-)tiles: both CTAs of a pair walk it
   const int n_seg = sched.num_segments();
   QQQ_TR_INIT();
 
@@ -191,13 +197,14 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_init(bar_fullt + 8 * i, 1);
       mbar_init(bar_emptyt + 8 * i, 1);
     }
+    // pair: the leader's weight-full and accumulator-empty barriers collect the arrivals of both CTAs
     for (int i = lane; i < kMaxASlots; i += 32) {
-      mbar_init(bar_afull + 8 * i, 4 * KSUB);
+      mbar_init(bar_afull + 8 * i, (4 * KSUB) << PAIR);
       mbar_init(bar_aempty + 8 * i, 1);
     }
     if (lane < 2) {
       mbar_init(bar_dfull + 8 * lane, 1);
-      mbar_init(bar_dempty + 8 * lane, n_epi);
+      mbar_init(bar_dempty + 8 * lane, n_epi << PAIR);
     }
     mbar_fence_init();
     __syncwarp();
@@ -222,6 +229,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   };
   // Weight producer state (warp 0): the first ring of stages is requested before TMEM allocation and the CTA-wide
   // barrier, the rest in the role loop below.
+  // a scheduled tile is (n super-tile, token tile): this CTA's 128-channel tile is n-tile 2*snt + rank of a pair
+  auto nt_of = [&](int tile) { return ((tile / p.m_tiles) << PAIR) + (int)rank; };
   int w_seg = 0, w_tile = 0, w_kb = 0, w_kb1 = 0, w_count = 0;
   Ring w_st(NSW);
   auto w_next = [&]() {  // advance to the next unit; false when the CTA's work is exhausted
@@ -233,18 +242,30 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   };
   if (warp == 0) {
     while (w_count < NSW && w_next()) {
-      if (elect_one()) issue_weights(w_st.idx, w_tile / p.m_tiles, w_kb);
+      if (elect_one()) issue_weights(w_st.idx, nt_of(w_tile), w_kb);
       __syncwarp();
       w_st.advance();
       ++w_kb;
       ++w_count;
     }
   }
-  if (warp == 1) tmem_alloc(smem_u32(&misc[0]), 512);
+  if (warp == 1) {
+    if (PAIR)
+      tmem_alloc_pair(smem_u32(&misc[0]), 512);
+    else
+      tmem_alloc(smem_u32(&misc[0]), 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // the peer's barriers are initialised and its TMEM is allocated before anything remote
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc[0];
+  // pair: barriers of the leader CTA that this CTA signals
+  const uint32_t lead_fullt = PAIR ? mapa_shared(bar_fullt, 0) : bar_fullt;
+  const uint32_t lead_afull = PAIR ? mapa_shared(bar_afull, 0) : bar_afull;
+  const uint32_t lead_dempty = PAIR ? mapa_shared(bar_dempty, 0) : bar_dempty;
   if (threadIdx.x == 0) QQQ_TR(12, 0);
 
   if (warp == 0) {
@@ -255,7 +276,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(bar_emptyw + 8 * w_st.idx, w_st.phase ^ 1);
       if (elect_one()) {
         QQQ_TR(0, w_count);
-        issue_weights(w_st.idx, w_tile / p.m_tiles, w_kb);
+        issue_weights(w_st.idx, nt_of(w_tile), w_kb);
         QQQ_TR(1, w_count);
       }
       __syncwarp();
@@ -275,19 +296,27 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         mbar_wait(bar_emptyt + 8 * st.idx, st.phase ^ 1);
         if (elect_one()) {
           const uint32_t full = bar_fullt + 8 * st.idx;
-          mbar_expect_tx(full, stage_t);
-          for (int sub = 0; sub < KSUB; ++sub)
-            tma_load_2d(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, full, (kb * KSUB + sub) * kBlockK,
-                        mt * p.n_tok, p.hint_a);
+          if (!PAIR) {
+            mbar_expect_tx(full, stage_t);
+            for (int sub = 0; sub < KSUB; ++sub)
+              tma_load_2d(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, full, (kb * KSUB + sub) * kBlockK,
+                          mt * p.n_tok, p.hint_a);
+          } else {
+            // both halves of the token tile are signalled on the leader's barrier (the MMA issuer waits there)
+            if (rank == 0) mbar_expect_tx(full, 2 * stage_t);
+            for (int sub = 0; sub < KSUB; ++sub)
+              tma_load_2d_pair(smem_u32(sT + st.idx * stage_t + sub * tok_bytes), &tmap_a, lead_fullt + 8 * st.idx,
+                               (kb * KSUB + sub) * kBlockK, mt * p.n_tok + (int)rank * tok_rows, p.hint_a);
+          }
         }
         __syncwarp();
         st.advance();
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
+  } else if (warp == 1 && rank == 0) {
+    // ===================================== MMA issuer (pair: the leader CTA only) ===========
     Ring st(NST), as(NA);
-    const uint32_t idesc = make_idesc_i8(kTileN, p.n_tok);
+    const uint32_t idesc = make_idesc_i8(kTileN << PAIR, p.n_tok);
     const uint64_t desc_tok0 = make_smem_desc(smem_u32(sT), 16, 1024, 2);  // + (byte offset >> 4) per stage / k-step
     int ucount = 0;
     for (int seg = 0; seg < n_seg; ++seg) {
@@ -307,15 +336,26 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           uint32_t tmem_a = tmem_base + tmem_a0 + as.idx * 32 * KSUB;
           for (int sub = 0; sub < KSUB; ++sub) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_i8_ts(tmem_d, tmem_a + ks * 8, desc + 2 * ks, idesc, (kb > kb0 || sub > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (kb > kb0 || sub > 0 || ks > 0) ? 1u : 0u;
+              if (PAIR)
+                umma_i8_ts_pair(tmem_d, tmem_a + ks * 8, desc + 2 * ks, idesc, acc);
+              else
+                umma_i8_ts(tmem_d, tmem_a + ks * 8, desc + 2 * ks, idesc, acc);
+            }
             desc += (uint64_t)(tok_bytes >> 4);
             tmem_a += 32;
           }
           // same thread as the MMAs above: tcgen05.commit tracks the issuing thread's operations
-          umma_commit(bar_aempty + 8 * as.idx);
-          umma_commit(bar_emptyt + 8 * st.idx);
-          if (kb == kb1 - 1) umma_commit(bar_dfull + 8 * dbuf);
+          if (PAIR) {  // the barriers at these offsets in BOTH CTAs of the pair
+            umma_commit_pair(bar_aempty + 8 * as.idx, 3);
+            umma_commit_pair(bar_emptyt + 8 * st.idx, 3);
+            if (kb == kb1 - 1) umma_commit_pair(bar_dfull + 8 * dbuf, 3);
+          } else {
+            umma_commit(bar_aempty + 8 * as.idx);
+            umma_commit(bar_emptyt + 8 * st.idx);
+            if (kb == kb1 - 1) umma_commit(bar_dfull + 8 * dbuf);
+          }
           QQQ_TR(6, ucount);
         }
         st.advance();
@@ -386,7 +426,10 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(bar_afull + 8 * as.idx);
+            if (PAIR)
+              mbar_arrive_cluster(lead_afull + 8 * as.idx);
+            else
+              mbar_arrive(bar_afull + 8 * as.idx);
             mbar_arrive(bar_emptyw + 8 * st.idx);  // this warp's reads of the weight stage are done
           }
           if (q == 0 && lane == 0) QQQ_TR(4, itn);
@@ -419,7 +462,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int seg = 0; seg < n_seg; ++seg) {
       int tile, kb0, kb1;
       sched.segment(seg, tile, kb0, kb1);
-      const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+      const int nt = nt_of(tile), mt = tile % p.m_tiles;
+      const int rtile = (tile << PAIR) + (int)rank;  // unique id of this CTA's 128-channel tile (scratch blocks)
       const int dbuf = seg % ndbuf;
       const uint32_t dph = (seg / ndbuf) & 1;
       const int n = nt * kTileN + 32 * q + lane;
@@ -434,8 +478,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // Partial tiles of split-K live in C as compact [n_tok][128] int32 blocks, block index =
       // (ticket * a_tiles + tile): a chunk's 16 rows are 512 B apart, so the 16 stores / loads of a lane use one base
       // register and immediate offsets (no serial address chain), and each of them is one full 128-byte line per warp.
-      int* __restrict__ cbase = p.C + (size_t)tile * tile_ints + 32 * q + lane;
-      const size_t ticket_stride = (size_t)p.a_tiles * tile_ints;  // split tiles are tiles [0, a_tiles)
+      int* __restrict__ cbase = p.C + (size_t)rtile * tile_ints + 32 * q + lane;
+      const size_t ticket_stride = (size_t)(p.a_tiles << PAIR) * tile_ints;  // split tiles are tiles [0, a_tiles)
 
       // per-token scales of this token tile -> smem (once per tile change), so the store loop has no global loads
       if (mt != staged_mt) {
@@ -549,7 +593,12 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dempty + 8 * dbuf);  // accumulator buffer may be overwritten
+      if (lane == 0) {  // accumulator buffer may be overwritten (pair: the leader's MMA issuer waits for both CTAs)
+        if (PAIR)
+          mbar_arrive_cluster(lead_dempty + 8 * dbuf);
+        else
+          mbar_arrive(bar_dempty + 8 * dbuf);
+      }
       if (epi_tid == 0) QQQ_TR(8, seg);
 
       if (!whole) {
@@ -567,38 +616,62 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while the other can still signal it or use its operands
+  else
+    __syncthreads();
   if (threadIdx.x == 0) QQQ_TR(12, 1);
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) {
+    if (PAIR)
+      tmem_dealloc_pair(tmem_base, 512);
+    else
+      tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace
 
 size_t gemm_smem_bytes(const GemmParams& p) {
-  return 1024 + kEpiStageBytes + (size_t)p.stages_t * p.ksub * p.n_tok * 128 + (size_t)p.stages_w * p.ksub * (kStageB + kStageS) +
+  return 1024 + kEpiStageBytes + (size_t)p.stages_t * p.ksub * (p.n_tok >> p.pair) * 128 +
+         (size_t)p.stages_w * p.ksub * (kStageB + kStageS) +
          8 * (2 * p.stages_w + 2 * p.stages_t + 2 * kMaxASlots + 4) + 16 + 4 * kMaxTok;
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
-  static bool attr_set[2][64] = {};  // the opt-in shared-memory attribute is per device
+  static bool attr_set[4][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
-  auto kern = grouped ? qqq_gemm_kernel<true> : qqq_gemm_kernel<false>;
-  if (dev < 0 || dev >= 64 || !attr_set[grouped][dev]) {
+  const int variant = (grouped ? 1 : 0) + (p.pair ? 2 : 0);
+  auto kern = variant == 0 ? qqq_gemm_kernel<false, false>
+            : variant == 1 ? qqq_gemm_kernel<true, false>
+            : variant == 2 ? qqq_gemm_kernel<false, true>
+                           : qqq_gemm_kernel<true, true>;
+  if (dev < 0 || dev >= 64 || !attr_set[variant][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_set[grouped][dev] = true;
+    if (dev >= 0 && dev < 64) attr_set[variant][dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // overlap launch + prologue + weight prefetch
-  attr[0].val.programmaticStreamSerializationAllowed = 1;           // with the tail of the preceding kernel
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // overlap launch + prologue + weight prefetch
+    attr[na].val.programmaticStreamSerializationAllowed = 1;           // with the tail of the preceding kernel
+    ++na;
+  }
+  if (p.pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;  // CTA pairs: two SMs of one TPC
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, tmap_a, tmap_b, p);
 }
 

@@ -40,6 +40,8 @@ struct GemmParams {
   int k_units;       // ceil(k_blocks / ksub): pipeline stages ("units") per tile
   int stages_w, stages_t;  // depth of the weight / token smem rings
   int unpack_groups;       // 2 or 3 groups of 4 unpack warps; the other 16-4G non-control warps are epilogue warps
+  int pair;                // 1: CTA pairs (cluster of 2, cta_group::2): scheduled tiles are 256 channels wide, each CTA of
+                           // a pair owns 128 of them and loads half of the token tile; n_tiles stays in 128-channel tiles
   // two-phase schedule (see Sched in qqq_gemm_sm100.cu); a unit = (tile, k-unit), tile = mt + m_tiles*nt
   int a_tiles;  // tiles [0, a_tiles) are cut along K: CTA b owns phase-A units [b*a_upc, (b+1)*a_upc) of a_units
   int a_units;  // a_tiles * k_units

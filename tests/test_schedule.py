@@ -10,11 +10,11 @@ import pytest
 from qqq_b200 import _lib
 
 KEYS = ["grid", "n_tok", "m_tiles", "n_tiles", "k_blocks", "ksub", "k_units", "a_tiles", "a_units", "a_upc", "b_tiles",
-        "b_tpc", "stages_w", "stages_t", "unpack_groups", "smem_bytes"]
+        "b_tpc", "stages_w", "stages_t", "unpack_groups", "smem_bytes", "pair", "_r1", "_r2", "_r3"]
 
 
 def plan(M, N, K, gs=-1, sms=148, max_par=16):
-    out = (ctypes.c_int * 16)()
+    out = (ctypes.c_int * 20)()
     rc = _lib.load().qqq_b200_plan(M, N, K, gs, sms, max_par, out)
     assert rc == 0
     return dict(zip(KEYS, out))
@@ -49,9 +49,12 @@ def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
     if gs == 128 and K % 128:
         pytest.skip("per-group needs K % 128 == 0")
     p = plan(M, N, K, gs, sms)
-    KU, tiles = p["k_units"], p["m_tiles"] * p["n_tiles"]
+    pair = p["pair"]  # CTA pairs: a scheduled tile is two adjacent 128-channel tiles, walked by two CTAs
+    assert pair in (0, 1) and (pair == 0 or (p["n_tiles"] % 2 == 0 and p["n_tok"] % 32 == 0 and p["grid"] % 2 == 0))
+    KU, tiles = p["k_units"], p["m_tiles"] * (p["n_tiles"] >> pair)
     assert p["a_tiles"] + p["b_tiles"] == tiles and p["a_units"] == p["a_tiles"] * KU
     assert 1 <= p["grid"] <= sms
+    p = dict(p, grid=p["grid"] >> pair)  # schedule indices
     assert p["n_tok"] % 16 == 0 and 16 <= p["n_tok"] <= 256 and p["m_tiles"] * p["n_tok"] >= M
     assert p["ksub"] in (1, 2, 4) and KU == -(-p["k_blocks"] // p["ksub"])
     assert p["smem_bytes"] <= 232448 and p["stages_w"] >= 2 and p["stages_t"] >= 2
@@ -85,10 +88,11 @@ def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
             assert t < p["a_tiles"]
             parts = (t * KU + KU - 1) // p["a_upc"] - (t * KU) // p["a_upc"] + 1
             assert parts == len(ctas)
-            last_block = (parts - 2) * p["a_tiles"] + t  # highest block index a contributor of this tile writes
+            # highest block index a contributor of this (pair of) tile(s) writes
+            last_block = (parts - 2) * (p["a_tiles"] << pair) + (t << pair) + pair
             assert (last_block + 1) * tile_ints <= 64 * 16 * N, "partial tiles do not fit C"
     if any(len(c) > 1 for c in contributors.values()):
-        assert tiles <= (N // 128) * 16, "not enough lock words in workspace"
+        assert (tiles << pair) <= (N // 128) * 16, "not enough lock words in workspace"
 
 
 def test_decode_plan_hides_the_fixup():
