@@ -1,0 +1,211 @@
+"""Model-level harness: module swap on a stock HF decoder, RTN quantizers in the reference
+Quantizer's conventions, checkpoint format, q/k/v + gate/up fusion.
+
+CPU tests: the product has no CPU path, so the two C-ABI entry points `QuantLinear.forward` calls are replaced — in the
+test only — by the oracle (`oracle_backend` fixture); what is under test here is the host logic around them.
+The same scenarios run on the real kernels in tests/test_zz_model_gpu.py.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import qqq_oracle as O
+
+transformers = pytest.importorskip("transformers")
+
+import qqq_b200  # noqa: E402
+from qqq_b200 import model as qmodel  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def tiny_config(model_type="llama", layers=2):
+    kw = dict(vocab_size=128, hidden_size=256, intermediate_size=512, num_hidden_layers=layers, num_attention_heads=4,
+              num_key_value_heads=2, max_position_embeddings=64, tie_word_embeddings=False)
+    if model_type == "llama":
+        return transformers.LlamaConfig(**kw)
+    return transformers.Qwen2Config(**kw)
+
+
+def tiny_model(model_type="llama", seed=0, dtype=torch.float16):
+    torch.manual_seed(seed)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)  # like from_pretrained(torch_dtype=...): rotary inv_freq stays fp32
+    try:
+        m = transformers.AutoModelForCausalLM.from_config(tiny_config(model_type))
+    finally:
+        torch.set_default_dtype(prev)
+    if model_type == "qwen2":  # from_config zero-initialises biases: give q/k/v real ones
+        for n, p in m.named_parameters():
+            if n.endswith("proj.bias"):
+                p.data.normal_(0, 0.05)
+    return m.eval()
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    """QuantLinear.forward on the CPU oracle (test infrastructure only)."""
+    from qqq_b200 import ops
+
+    def dq(x):
+        q, s = O.dynamic_quant(x.detach().cpu().numpy(), cuda_semantics=True)
+        return torch.from_numpy(q), torch.from_numpy(s)
+
+    def gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1, max_par=8):
+        ref = O.qqq_gemm_oracle(A.numpy(), B.numpy(), s1.numpy(), s2.numpy(), s3.numpy() if s3.numel() else None)
+        D.copy_(torch.from_numpy(ref))
+
+    monkeypatch.setattr(ops, "dynamic_quant", dq)
+    monkeypatch.setattr(ops, "qqq_gemm", gemm)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RTN quantizer vs the reference Quantizer (golden fixtures from tests/golden/gen_rtn_golden.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "rtn_*.npz"))), ids=os.path.basename)
+def test_rtn_quantizer_matches_reference_quantizer(path):
+    g = np.load(path)
+    gs = -1 if path.endswith("gpc.npz") else 128
+    W_fq, scale, zero, s_extra = qmodel.rtn_quantize_weight(torch.from_numpy(g["W"]), gs)
+    assert np.array_equal(scale.numpy(), g["scale"])
+    assert np.array_equal(zero.numpy(), g["zero"])
+    assert np.array_equal(W_fq.numpy(), g["Q"])
+    if gs != -1:
+        assert np.array_equal(s_extra.numpy(), g["s_extra"])
+    else:
+        assert s_extra is None
+
+
+def test_rtn_fixture_set_is_present():
+    assert len(glob.glob(os.path.join(GOLDEN, "rtn_*.npz"))) >= 4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# module swap
+# ---------------------------------------------------------------------------------------------------------------
+def test_find_layers_and_decoder_names():
+    m = tiny_model()
+    lin = qmodel.find_layers(m)
+    assert "lm_head" in lin and len(lin) == 2 * 7 + 1
+    names = list(qmodel.decoder_linear_names(m))
+    assert len(names) == 14 and "lm_head" not in names
+    assert "model.layers.1.mlp.down_proj" in names and "model.layers.0.self_attn.k_proj" in names
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_make_quant_swaps_by_name_and_keeps_the_rest(gs):
+    m = tiny_model()
+    names = list(qmodel.decoder_linear_names(m))
+    qmodel.make_quant(m, names, 4, gs)
+    ql = qmodel.find_layers(m, [qqq_b200.QuantLinear])
+    assert sorted(ql) == sorted(names)
+    assert type(m.lm_head) is nn.Linear and type(m.model.embed_tokens) is nn.Embedding
+    k = ql["model.layers.0.self_attn.k_proj"]
+    assert (k.infeatures, k.outfeatures) == (256, 128) and k.bias is None
+    assert k.B.shape == (16, 256) and k.s_channel.shape == (1, 128)
+    assert k.s_group.shape == ((2, 128) if gs == 128 else (0,))
+    # checkpoint keys are the reference's: <name>.B / .s_channel / .s_group (no workspace / reduce_buffer)
+    keys = set(qmodel.quantized_state_dict(m))
+    assert "model.layers.0.self_attn.k_proj.B" in keys and "model.layers.0.self_attn.k_proj.s_channel" in keys
+    assert ("model.layers.0.self_attn.k_proj.s_group" in keys) == (gs == 128)
+    assert not any(k.endswith("workspace") or k.endswith("reduce_buffer") or k.endswith("proj.weight") for k in keys)
+
+
+def test_make_quant_is_a_noop_on_a_quantlinear_and_rejects_other_modules():
+    ql = qqq_b200.QuantLinear(4, -1, 128, 64, bias=False)
+    qmodel.make_quant(ql, ["x"], 4, -1)
+    m = tiny_model()
+    with pytest.raises(NotImplementedError):
+        qmodel.make_quant(m, ["model.embed_tokens"], 4, -1)
+
+
+def test_unsupported_architecture_raises_like_the_reference_registry():
+    with pytest.raises(NotImplementedError):
+        qmodel.get_model_architecture(transformers.GPT2Config())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole-model scenarios on the oracle backend
+# ---------------------------------------------------------------------------------------------------------------
+def _logits(m, ids):
+    with torch.no_grad():
+        return m(input_ids=ids).logits.float()
+
+
+@pytest.mark.parametrize("model_type,gs", [("llama", -1), ("llama", 128), ("qwen2", 128)])
+def test_quantized_model_tracks_the_fake_quant_model(oracle_backend, model_type, gs):
+    """W4A8 logits vs the fake-quantized fp16 model (same weights, fp16 activations): only the int8 activation
+    rounding and the int8 re-quantisation of per-group weights separate them."""
+    m = tiny_model(model_type)
+    ids = torch.randint(0, 128, (2, 12), generator=torch.Generator().manual_seed(1))
+    quantizers = qmodel.rtn_quantizers(m, gs)
+    ref = _logits(m, ids)  # weights are fake-quantized in place now
+    qmodel.pack_model(m, quantizers, 4, gs)
+    assert len(qmodel.find_layers(m, [qqq_b200.QuantLinear])) == 14
+    got = _logits(m, ids)
+    err = (got - ref).abs().max().item()
+    assert err <= 0.05 * ref.abs().max().item() + 0.02, err
+    if model_type == "qwen2":
+        assert m.model.layers[0].self_attn.q_proj.bias is not None
+
+
+@pytest.mark.parametrize("model_type,gs", [("llama", -1), ("qwen2", 128)])
+def test_fused_qkv_gate_up_is_bit_identical(oracle_backend, model_type, gs):
+    m = qmodel.quantize_model_rtn(tiny_model(model_type), gs)
+    ids = torch.randint(0, 128, (1, 9), generator=torch.Generator().manual_seed(2))
+    before = _logits(m, ids)
+    n_before = len(qmodel.find_layers(m, [qqq_b200.QuantLinear]))
+    assert qmodel.fuse_qkv_gate_up(m) == 4  # 2 layers x (qkv, gate_up)
+    ql = qmodel.find_layers(m, [qqq_b200.QuantLinear])
+    assert n_before == 14 and len(ql) == 2 * 4  # qkv, o, gate_up, down per layer
+    assert isinstance(m.model.layers[0].self_attn.k_proj, qmodel.FusedProjection)
+    after = _logits(m, ids)
+    assert torch.equal(before, after)
+    # a second forward with another input must not reuse the cached merged output
+    ids2 = torch.randint(0, 128, (1, 9), generator=torch.Generator().manual_seed(3))
+    assert not torch.equal(_logits(m, ids2), after)
+    assert torch.equal(_logits(m, ids), after)
+
+
+def test_fused_projection_runs_one_gemm_per_group(oracle_backend, monkeypatch):
+    from qqq_b200 import ops
+
+    m = qmodel.quantize_model_rtn(tiny_model("llama"), -1)
+    qmodel.fuse_qkv_gate_up(m)
+    calls = []
+    inner = ops.qqq_gemm
+    monkeypatch.setattr(ops, "qqq_gemm", lambda *a, **k: (calls.append(a[3].shape[-1]), inner(*a, **k))[1])
+    _logits(m, torch.randint(0, 128, (1, 5)))
+    assert len(calls) == 2 * 4 and sorted(set(calls)) == [256, 512, 1024]  # qkv 256+128+128, o/down 256, gate_up 1024
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_checkpoint_round_trip(oracle_backend, gs, tmp_path):
+    m = qmodel.quantize_model_rtn(tiny_model("llama"), gs)
+    assert m.config.quantization_config == {"group_size": gs, "quant_method": "qqq", "wbits": 4}
+    sd = qmodel.quantized_state_dict(m)
+    assert all(v.numel() > 0 for v in sd.values())
+    torch.save(sd, tmp_path / "model.pt")
+    m2 = qmodel.build_quantized_model(tiny_config("llama"), m.config.quantization_config)
+    assert len(qmodel.find_layers(m2, [qqq_b200.QuantLinear])) == 14
+    qmodel.load_quantized_state_dict(m2, torch.load(tmp_path / "model.pt"))
+    ids = torch.randint(0, 128, (1, 7), generator=torch.Generator().manual_seed(5))
+    assert torch.equal(_logits(m, ids), _logits(m2.eval(), ids))
+    bad = dict(sd)
+    bad["model.layers.0.mlp.up_proj.qweight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        qmodel.load_quantized_state_dict(m2, bad)
+    short = {k: v for k, v in sd.items() if not k.endswith("down_proj.B")}
+    with pytest.raises(RuntimeError):
+        qmodel.load_quantized_state_dict(m2, short)
+
+
+def test_product_forward_has_no_cpu_path():
+    """Without the oracle fixture the swapped model must refuse to run on the CPU (no silent fallback)."""
+    m = qmodel.quantize_model_rtn(tiny_model("llama"), -1)
+    with pytest.raises(RuntimeError):
+        _logits(m, torch.randint(0, 128, (1, 4)))
