@@ -351,6 +351,74 @@ def cpu_baseline(steps=2, warmup=1):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# configs[2]: Llama-3-8B per-group g=128, decode batch=32 seq=1 (reported beside the headline, not the headline)
+# ----------------------------------------------------------------------------------------------------------
+LLAMA3_8B = dict(name="llama-3-8b", layers=32, hidden=4096, inter=14336, kv=1024, batch=32)
+LLAMA3_LINEARS = [("q", "hidden", "hidden"), ("k", "hidden", "kv"), ("v", "hidden", "kv"), ("o", "hidden", "hidden"),
+                  ("gate", "hidden", "inter"), ("up", "hidden", "inter"), ("down", "inter", "hidden")]
+
+
+def decode_g128(dev, peaks, steps, warmup):
+    """All 224 quantized linears of Llama-3-8B (g128) on a batch of 32 single-token rows, replayed from one CUDA
+    graph: per layer 7 x (act-quant + GEMM), and the merged q/k/v + gate/up variant.  HBM-bound: the figure of merit is
+    algorithmic bytes / time against the measured HBM peak."""
+    import qqq_b200
+    from qqq_b200 import graph as qgraph
+
+    cfg, M = LLAMA3_8B, LLAMA3_8B["batch"]
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    layers, by = [], 0.0
+    for _ in range(cfg["layers"]):
+        mods = {}
+        for (name, k, n) in LLAMA3_LINEARS:
+            K, N = cfg[k], cfg[n]
+            ql = qqq_b200.QuantLinear(4, 128, K, N, bias=False).to(dev)
+            ql.B = random_packed(K, N, gen, dev)
+            ql.s_group = (torch.rand(K // 128, N, device=dev, generator=gen) * 8 + 4).half()
+            ql.s_channel = torch.full((1, N), 1.0 / (8 * 4.6 * (K ** 0.5)), dtype=torch.float32, device=dev)
+            mods[name] = ql
+            by += M * K + K * N / 2 + 2 * M * N + 4 * M + 4 * N + 2 * (K // 128) * N
+        layers.append(mods)
+
+    def chain(h):
+        for m in layers:
+            q = m["q"](h)
+            m["k"](h)
+            m["v"](h)
+            o = m["o"](q)
+            g = m["gate"](o)
+            m["up"](o)
+            h = m["down"](g)
+        return h
+
+    x = torch.randn(M, cfg["hidden"], device=dev, generator=gen).half()
+    none = lambda: None  # noqa: E731
+    g = qgraph.capture(chain, x)
+    ms = timed(lambda: g(x), steps, warmup, none)
+    out = dict(workload="llama-3-8b decode batch=32 seq=1: all 224 quantized linears, per-group g=128, 7 x (act-quant + GEMM) "
+                        "per layer; random-init weights; 3.6 GB of packed weights + group scales stream from HBM every step",
+               ms_per_step=round(ms, 4), value=round(M / (ms * 1e-3), 1), unit="tokens/s",
+               gbps=round(by / (ms * 1e-3) / 1e9, 1), hbm_frac=round(by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 3),
+               algorithmic_bytes_per_step=by)
+    del g
+    mlayers = [dict(qkv=qqq_b200.merge_quant_linears([m["q"], m["k"], m["v"]]), o=m["o"],
+                    gate_up=qqq_b200.merge_quant_linears([m["gate"], m["up"]]), down=m["down"]) for m in layers]
+
+    def chain_merged(h):
+        for m in mlayers:
+            qkv = m["qkv"](h)
+            o = m["o"](qkv[:, : m["qkv"].split_sizes[0]])
+            gu = m["gate_up"](o)
+            h = m["down"](gu[:, : m["gate_up"].split_sizes[0]])
+        return h
+
+    gm = qgraph.capture(chain_merged, x)
+    ms_m = timed(lambda: gm(x), steps, warmup, none)
+    out["merged"] = dict(ms_per_step=round(ms_m, 4), value=round(M / (ms_m * 1e-3), 1))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -360,6 +428,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-merged", action="store_true", help="skip the merged QKV / gate-up variant (profiler runs)")
+    ap.add_argument("--no-decode", action="store_true", help="skip the Llama-3-8B g128 decode section (configs[2])")
+    ap.add_argument("--aux-budget", type=float, default=600.0, help="seconds the auxiliary sections may take in total")
     args = ap.parse_args()
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
@@ -494,10 +564,34 @@ def main():
                         note="same weights with q/k/v and gate/up merged by concatenating their packed tensors "
                              "(qqq_b200.merge_quant_linears, bit-identical outputs): 4 act-quants + 4 GEMMs per layer"),
                     roofline=roofline, tflops_linears=round(flops_rank * world / (ms * 1e-3) / 1e12, 1))
+        # Auxiliary sections: each guarded, all under one watchdog, so that neither an exception nor a stall in them
+        # can cost the headline line above.
+        aux = []
+        if world == 1 and not args.no_cpu:  # first: the contract's cpu_baseline must not fall to the watchdog
+            aux.append(("cpu_baseline", lambda: cpu_baseline()[0]))
         if world == 1 and not args.no_sweep:
-            line["gemm_sweep"] = gemm_sweep(dev, peaks)
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"], _ = cpu_baseline()
+            aux.append(("gemm_sweep", lambda: gemm_sweep(dev, peaks)))
+        if world == 1 and not args.no_decode:
+            aux.append(("decode_g128", lambda: decode_g128(dev, peaks, args.steps, args.warmup)))
+
+        def emit_and_exit():
+            line["aux_timeout_s"] = args.aux_budget
+            try:
+                print(json.dumps(line))
+            except Exception:
+                print(json.dumps({k: v for k, v in list(line.items()) if k not in dict(aux)}))
+            sys.stdout.flush()
+            os._exit(0)
+
+        wd = threading.Timer(args.aux_budget, emit_and_exit)
+        wd.daemon = True
+        wd.start()
+        for key, fn in aux:
+            try:
+                line[key] = fn()
+            except Exception as e:  # reported, never fatal
+                line[key] = {"error": repr(e)[:300]}
+        wd.cancel()
         print(json.dumps(line))
     if world > 1:
         # CUDA graphs captured above hold references into the NCCL communicator; tearing the process group down
