@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import torch
 
+from .qlinear import _ActQuantCache
+
 
 class GraphedCallable:
     def __init__(self, fn, example_input: torch.Tensor, warmup: int = 2, pool=None):
@@ -20,9 +22,13 @@ class GraphedCallable:
                 fn(self.static_in)
         torch.cuda.current_stream(example_input.device).wait_stream(side)
         torch.cuda.synchronize(example_input.device)
+        # an activation-quant cache entry from the warm-up (or from eager code) must not be "hit" during capture: the
+        # graph would then read int8 activations it never produces
+        _ActQuantCache.clear()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, pool=pool):
             self.static_out = fn(self.static_in)
+        _ActQuantCache.clear()
 
     def __call__(self, x: torch.Tensor = None) -> torch.Tensor:
         if x is not None and x.data_ptr() != self.static_in.data_ptr():

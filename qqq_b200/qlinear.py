@@ -71,6 +71,43 @@ def pack_int4_weights(w: torch.Tensor, per_group: bool) -> torch.Tensor:
     return word.to(torch.int32)
 
 
+class _ActQuantCache:
+    """Last (input -> int8, scale) pair of `dynamic_quant`, so that linears that consume the SAME tensor (q/k/v,
+    gate/up in the reference's 7-module layer structure) quantise it once.  Opt-in (`set_act_quant_cache(True)`):
+    a hit needs the same storage, offset, shape, strides, dtype AND tensor version, and the cached input is kept alive
+    so its address cannot be recycled — but a writer that bypasses autograd's version counter (a raw-pointer kernel
+    writing into the tensor between two forwards) is invisible to it."""
+
+    enabled = False
+    _key = None
+    _ref = None
+    _val = None
+
+    @classmethod
+    def key(cls, x):
+        return (x.untyped_storage().data_ptr(), x.storage_offset(), tuple(x.shape), tuple(x.stride()), x.dtype, x._version,
+                x.device)
+
+    @classmethod
+    def get(cls, x):
+        return cls._val if cls._key is not None and cls._key == cls.key(x) else None
+
+    @classmethod
+    def put(cls, x, val):
+        cls._key, cls._ref, cls._val = cls.key(x), x, val
+
+    @classmethod
+    def clear(cls):
+        cls._key = cls._ref = cls._val = None
+
+
+def set_act_quant_cache(enabled: bool) -> None:
+    """Reuse the int8 activations across consecutive QuantLinear.forward calls on the same input tensor (bit-identical
+    outputs, 3 of the 7 activation-quant launches of a decoder layer instead of 7).  Off by default."""
+    _ActQuantCache.enabled = bool(enabled)
+    _ActQuantCache.clear()
+
+
 class QuantLinear(nn.Module):
     QUANT_TYPE = "marlin"
 
@@ -185,7 +222,13 @@ class QuantLinear(nn.Module):
     def forward(self, A):
         out_shape = A.shape[:-1] + (self.outfeatures,)
         A = A.reshape(-1, A.shape[-1]).half()
-        quant_A, s1 = self.dynamic_quant(A)
+        cached = _ActQuantCache.get(A) if _ActQuantCache.enabled else None
+        if cached is not None:
+            quant_A, s1 = cached
+        else:
+            quant_A, s1 = self.dynamic_quant(A)
+            if _ActQuantCache.enabled:
+                _ActQuantCache.put(A, (quant_A, s1))
         D = torch.empty(A.shape[0], self.outfeatures, dtype=A.dtype, device=A.device)
         mul(quant_A, self.B, self.reduce_buffer, D, s1, self.s_channel, self.s_group, self.workspace,
             max_par=self.max_par)
@@ -225,4 +268,4 @@ def merge_quant_linears(mods) -> QuantLinear:
 
 QQQLinear = QuantLinear
 
-__all__ = ["QuantLinear", "QQQLinear", "mul", "pack_int4_weights", "merge_quant_linears"]
+__all__ = ["QuantLinear", "QQQLinear", "mul", "pack_int4_weights", "merge_quant_linears", "set_act_quant_cache"]

@@ -209,3 +209,40 @@ def test_product_forward_has_no_cpu_path():
     m = qmodel.quantize_model_rtn(tiny_model("llama"), -1)
     with pytest.raises(RuntimeError):
         _logits(m, torch.randint(0, 128, (1, 4)))
+
+
+def test_act_quant_cache_reuses_the_shared_input_only(oracle_backend, monkeypatch):
+    """Opt-in cache: q/k/v (and gate/up) quantise their shared input once; any change of the input (new tensor, in-place
+    write, other view) misses; outputs are bit-identical."""
+    from qqq_b200 import ops
+
+    m = qmodel.quantize_model_rtn(tiny_model("llama"), 128)
+    ids = torch.randint(0, 128, (1, 6), generator=torch.Generator().manual_seed(8))
+    ref = _logits(m, ids)
+    calls = []
+    inner = ops.dynamic_quant
+    monkeypatch.setattr(ops, "dynamic_quant", lambda x: (calls.append(1), inner(x))[1])
+    _logits(m, ids)
+    assert len(calls) == 14
+    qqq_b200.set_act_quant_cache(True)
+    try:
+        calls.clear()
+        assert torch.equal(_logits(m, ids), ref)
+        assert len(calls) == 2 * 4  # per layer: (q,k,v) once, o, (gate,up) once, down
+        ql = m.model.layers[0].self_attn.q_proj
+        x = torch.randn(3, 256).half()
+        calls.clear()
+        y0 = ql(x)
+        ql(x)
+        assert len(calls) == 1
+        x.mul_(2.0)  # in-place write bumps the version: miss
+        y1 = ql(x)
+        assert len(calls) == 2 and not torch.equal(y0, y1)
+        ql(x[1:])  # another view: miss
+        ql(x.clone())  # another storage: miss
+        assert len(calls) == 4
+    finally:
+        qqq_b200.set_act_quant_cache(False)
+    calls.clear()
+    ql(x), ql(x)
+    assert len(calls) == 2

@@ -80,3 +80,20 @@ def test_fused_qkv_gate_up_is_bit_identical_on_gpu(model_type, gs):
     torch.cuda.synchronize()
     assert qqq_b200.launch_count() - l0 == 2 * 8  # qkv, o, gate_up, down per layer
     assert torch.equal(before, after)
+
+
+def test_act_quant_cache_on_gpu_is_bit_identical_and_saves_launches():
+    import qqq_b200
+
+    m, _ = _quantized_on_gpu("llama", -1)
+    ids = torch.arange(11, device="cuda:0").reshape(1, 11) * 5 % 128
+    ref = _logits(m, ids)
+    qqq_b200.set_act_quant_cache(True)
+    try:
+        l0 = qqq_b200.launch_count()
+        got = _logits(m, ids)
+        torch.cuda.synchronize()
+        assert qqq_b200.launch_count() - l0 == 14 + 8  # 14 GEMMs, 4 activation quants per layer
+    finally:
+        qqq_b200.set_act_quant_cache(False)
+    assert torch.equal(ref, got)
