@@ -159,22 +159,27 @@ def build_model(dev, rank, world, gen):
     return layers
 
 
+def _all_reduce_after(mod, y, world):
+    """NCCL all-reduce after a row-parallel linear — unless the module reduces in its own epilogue (--fused-allreduce)."""
+    import torch.distributed as dist
+    from qqq_b200 import tp
+
+    if world > 1 and not isinstance(mod, tp.FusedRowParallelQuantLinear):
+        dist.all_reduce(y)
+
+
 def forward_chain(layers, h, world):
     """The reference's module structure: 7 separate linears per layer (q, k, v re-quantise the same input)."""
-    import torch.distributed as dist
-
     for m in layers:
         q = m["q"](h)
         m["k"](h)
         m["v"](h)
         o = m["o"](q)
-        if world > 1:
-            dist.all_reduce(o)
+        _all_reduce_after(m["o"], o, world)
         g = m["gate"](o)
         m["up"](o)
         d = m["down"](g)
-        if world > 1:
-            dist.all_reduce(d)
+        _all_reduce_after(m["down"], d, world)
         h = d
     return h
 
@@ -192,19 +197,15 @@ def merge_layers(layers):
 
 
 def forward_chain_merged(mlayers, h, world):
-    import torch.distributed as dist
-
     for m in mlayers:
         qkv = m["qkv"](h)
         q = qkv[:, : m["qkv"].split_sizes[0]]  # column slice, consumed in place by the strided activation quant
         o = m["o"](q)
-        if world > 1:
-            dist.all_reduce(o)
+        _all_reduce_after(m["o"], o, world)
         gu = m["gate_up"](o)
         g = gu[:, : m["gate_up"].split_sizes[0]]
         d = m["down"](g)
-        if world > 1:
-            dist.all_reduce(d)
+        _all_reduce_after(m["down"], d, world)
         h = d
     return h
 
@@ -218,7 +219,7 @@ def gemm_only_chain(mlayers, qin):
 
     for m in mlayers:
         for name in GEMM_NAMES:
-            ql = m[name]
+            ql = getattr(m[name], "shard", m[name])
             A8, s1, D = qin[(ql.infeatures, ql.outfeatures)]
             qqq_b200.qqq_gemm(A8, ql.B, ql.reduce_buffer, D, s1, ql.s_channel, ql.s_group, ql.workspace, -1, -1, -1, 16)
 
@@ -428,6 +429,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-merged", action="store_true", help="skip the merged QKV / gate-up variant (profiler runs)")
+    ap.add_argument("--fused-allreduce", action="store_true",
+                    help="N > 1: row-parallel linears reduce in their own epilogue (tp.FusedRowParallelQuantLinear)")
     ap.add_argument("--no-decode", action="store_true", help="skip the Llama-3-8B g128 decode section (configs[2])")
     ap.add_argument("--aux-budget", type=float, default=600.0, help="seconds the auxiliary sections may take in total")
     args = ap.parse_args()
@@ -469,6 +472,16 @@ def main():
     peaks = load_peaks()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     layers = build_model(dev, rank, world, gen)
+    if args.fused_allreduce and world > 1:
+        # o_proj / down_proj add their output tiles into a multicast buffer from the GEMM epilogue (multimem.red over
+        # NVSwitch) instead of being followed by an NCCL all-reduce
+        from qqq_b200 import tp
+
+        ar_ws = tp.AllReduceWorkspace(M, MODEL["hidden"], device=torch.device(dev))
+        for m in layers:
+            m["o"] = tp.FusedRowParallelQuantLinear(m["o"], ar_ws)
+            m["down"] = tp.FusedRowParallelQuantLinear(m["down"], ar_ws)
+        cfg["parallelism"] += " (all-reduce fused into the GEMM epilogue, multimem.red)"
     x_host = (torch.randn(M, MODEL["hidden"], generator=torch.Generator().manual_seed(7))).half().pin_memory()
     out_host = torch.empty(M, MODEL["hidden"], dtype=torch.float16).pin_memory()
     x_dev = x_host.to(dev)
@@ -518,7 +531,7 @@ def main():
     # --- dominant kernel alone: the 224 GEMM launches on pre-quantised inputs ---
     qin = {}
     for name in GEMM_NAMES:
-        ql = layers[0][name]
+        ql = getattr(layers[0][name], "shard", layers[0][name])
         key = (ql.infeatures, ql.outfeatures)
         if key not in qin:
             A8 = torch.randint(-127, 128, (M, key[0]), dtype=torch.int8, device=dev)

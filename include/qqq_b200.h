@@ -51,6 +51,21 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
                     int dev, void* stream /* cudaStream_t */, int thread_k, int thread_n, int sms, int max_par);
 
 /*
+ * Tensor-parallel row shards (new work: the reference has no tensor parallelism): the same GEMM on this
+ * rank's K-shard, but every 16-byte piece of the output is ADDED (fp16, `multimem.red`) into `D_multicast` instead of
+ * stored.  `D_multicast` is the multicast address (cuMulticast* / NVLS, e.g. torch symmetric memory's `multicast_ptr`) of
+ * an fp16 [M,N] buffer replicated on every rank of the tensor-parallel group: the NVSwitch applies each add to every
+ * replica, so when all ranks' launches have completed, each replica holds the all-reduced output — the all-reduce
+ * that follows o_proj / down_proj rides in the GEMM epilogue.  The caller zeroes its replica beforehand and separates
+ * producers from consumers with a cross-rank barrier (qqq_b200/tp.py: FusedRowParallelQuantLinear).  All other
+ * arguments, the scratch contract and the return codes are those of qqq_gemm_sm100a; s1 are this rank's per-shard
+ * token scales.
+ */
+int qqq_gemm_reduce_sm100a(const void* A, const void* B, void* C, void* D_multicast, const void* s1, const void* s2,
+                           const void* s3, int prob_m, int prob_n, int prob_k, void* workspace, int groupsize,
+                           int dev, void* stream /* cudaStream_t */, int thread_k, int thread_n, int sms, int max_par);
+
+/*
  * Per-token dynamic int8 quantisation of activations, bit-identical to
  * QQQ/gptq/qlinear/qlinear_marlin.py:265-268:
  *   s1[m] = fp32( fp16( max_k |x[m,k]| / 127 ) );   q[m,k] = int8( clamp( rint( x[m,k] / s1[m] ), -128, 127 ) )

@@ -166,7 +166,7 @@ bool reference_shape_ok(int n, int k, int thread_k, int thread_n) {
 // Pure host-side planning (no CUDA calls): tiling, pipeline depths and the two-phase schedule for a problem on
 // `sm_count` SMs.  Exported as qqq_b200_plan() so the schedule can be checked exhaustively on a CPU-only machine.
 int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool has_scratch, qqq::GemmParams& p,
-              int* grid_out) {
+              int* grid_out, bool allow_pair = true) {
   using namespace qqq;
   p.M = M;
   p.N = N;
@@ -215,7 +215,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   // N = 21760), neutral at ~2 tiles per SM, slower when there is at most one tile per SM or the tiles are small.
   // QQQ_B200_PAIR=0/1 overrides the policy (1: wherever the shape allows it).
   static const int env_pair = getenv("QQQ_B200_PAIR") ? atoi(getenv("QQQ_B200_PAIR")) : -1;
-  const bool pair_ok = p.n_tiles % 2 == 0 && p.n_tok % 32 == 0 && sm_count >= 2;
+  const bool pair_ok = allow_pair && p.n_tiles % 2 == 0 && p.n_tok % 32 == 0 && sm_count >= 2;
   const bool pair_auto = p.n_tok == kMaxTok && p.m_tiles >= 2 && 2ll * p.m_tiles * p.n_tiles >= 5ll * sm_count;
   p.pair = (pair_ok && (env_pair == 1 || (env_pair != 0 && pair_auto))) ? 1 : 0;
   const int sched_cols = p.n_tiles >> p.pair;   // scheduled (super-)tiles per token tile
@@ -359,9 +359,9 @@ int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_coun
   return QQQ_OK;
 }
 
-int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
-                    int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
-                    int thread_k, int thread_n, int sms, int max_par) {
+static int gemm_impl(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
+                     int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
+                     int thread_k, int thread_n, int sms, int max_par, bool reduce) {
   using namespace qqq;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int M = prob_m, N = prob_n, K = prob_k;
@@ -425,9 +425,11 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   const int sm_count = (sms > 0 && sms < di->sms) ? sms : di->sms;
   int grid = 0;
   {
-    const int rc = plan_gemm(M, N, K, grouped, sm_count, max_par, C != nullptr && workspace != nullptr, p, &grid);
+    const int rc = plan_gemm(M, N, K, grouped, sm_count, max_par, C != nullptr && workspace != nullptr, p, &grid,
+                             /*allow_pair=*/!reduce);
     if (rc != QQQ_OK) return rc;
   }
+  p.reduce = reduce ? 1 : 0;
   // weights are streamed once when a single token tile covers M; tokens are re-read by every CTA
   p.hint_b = p.m_tiles == 1 ? kEvictFirst : kEvictNormal;
   p.hint_a = kEvictLast;
@@ -449,6 +451,20 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
   }
   g_launches.fetch_add(1);
   return QQQ_OK;
+}
+
+int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
+                    int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
+                    int thread_k, int thread_n, int sms, int max_par) {
+  return gemm_impl(A, B, C, D, s1, s2, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, thread_k, thread_n,
+                   sms, max_par, false);
+}
+
+int qqq_gemm_reduce_sm100a(const void* A, const void* B, void* C, void* D_multicast, const void* s1, const void* s2,
+                           const void* s3, int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev,
+                           void* stream_, int thread_k, int thread_n, int sms, int max_par) {
+  return gemm_impl(A, B, C, D_multicast, s1, s2, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, thread_k,
+                   thread_n, sms, max_par, true);
 }
 
 int qqq_act_quant_strided_sm100a(const void* x, long long ldx, void* q, void* s1, int prob_m, int prob_k, int dev,

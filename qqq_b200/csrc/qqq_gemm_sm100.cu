@@ -134,7 +134,23 @@ __device__ __forceinline__ uint32_t unpack_pg4(uint32_t w, uint32_t s2h) {
   return out;
 }
 
-template <bool GROUPED, bool kPair>
+// How a finished 16-byte piece of an output row leaves the SM.  kReduce = false: a plain store into D.
+// kReduce = true (tensor-parallel row shards, qqq_gemm_reduce_sm100a): D is a MULTICAST address bound to the same
+// buffer on every rank; `multimem.red` adds the eight fp16 values into every replica (the NVSwitch fans the
+// reduction out), so once all ranks' kernels have finished every replica holds the all-reduced output — the
+// collective rides in the epilogue instead of following the GEMM as a separate NCCL call.
+template <bool kReduce>
+__device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
+  if constexpr (kReduce) {
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(dp), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+  } else {
+    *reinterpret_cast<uint4*>(dp) = v;
+  }
+}
+
+template <bool GROUPED, bool kPair, bool kReduce = false>
 __global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
@@ -559,8 +575,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint4* rp = reinterpret_cast<const uint4*>(stg) + lane;  // row st_tok, part st_part
             const uint4 v0 = rp[0], v1 = rp[32];                            // rows st_tok and st_tok + 8
             __half* dp = p.D + (size_t)(m0 + mb + st_tok) * p.N + (nt * kTileN + 32 * q + 8 * st_part);
-            if (mb + st_tok < rows) *reinterpret_cast<uint4*>(dp) = v0;
-            if (mb + st_tok + 8 < rows) *reinterpret_cast<uint4*>(dp + (size_t)8 * p.N) = v1;
+            if (mb + st_tok < rows) emit_d<kReduce>(dp, v0);
+            if (mb + st_tok + 8 < rows) emit_d<kReduce>(dp + (size_t)8 * p.N, v1);
           }
           __syncwarp();  // the tile is rewritten by the next chunk
         } else {
@@ -639,13 +655,16 @@ size_t gemm_smem_bytes(const GemmParams& p) {
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
-  static bool attr_set[4][64] = {};  // the opt-in shared-memory attribute is per device
+  static bool attr_set[6][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
-  const int variant = (grouped ? 1 : 0) + (p.pair ? 2 : 0);
+  if (p.reduce && p.pair) return cudaErrorInvalidValue;  // the planner never pairs a reducing launch
+  const int variant = p.reduce ? 4 + (grouped ? 1 : 0) : (grouped ? 1 : 0) + (p.pair ? 2 : 0);
   auto kern = variant == 0 ? qqq_gemm_kernel<false, false>
             : variant == 1 ? qqq_gemm_kernel<true, false>
             : variant == 2 ? qqq_gemm_kernel<false, true>
-                           : qqq_gemm_kernel<true, true>;
+            : variant == 3 ? qqq_gemm_kernel<true, true>
+            : variant == 4 ? qqq_gemm_kernel<false, false, true>
+                           : qqq_gemm_kernel<true, false, true>;
   if (dev < 0 || dev >= 64 || !attr_set[variant][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) return e;

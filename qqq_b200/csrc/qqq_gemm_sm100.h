@@ -49,6 +49,7 @@ struct GemmParams {
   int b_tiles;  // tiles [a_tiles, a_tiles + b_tiles) are processed whole: CTA b owns b_tpc consecutive ones
   int b_tpc;
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
+  int reduce;               // 1: D is a multicast address and the epilogue adds into it (multimem.red) instead of storing
 };
 
 size_t gemm_smem_bytes(const GemmParams& p);

@@ -73,6 +73,28 @@ def qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1
         raise RuntimeError(f"qqq_gemm_sm100a failed (rc={err}): {_lib.last_error()}")
 
 
+def qqq_gemm_reduce(A, B, C, d_multicast_ptr: int, s1, s2, s3, workspace, prob_n: int, max_par=16, sms=-1):
+    """Row-shard GEMM whose epilogue ADDS its fp16 output into the multicast address `d_multicast_ptr` (an fp16 [M, prob_n]
+    buffer replicated on every rank of the tensor-parallel group) instead of storing it: qqq_gemm_reduce_sm100a in
+    include/qqq_b200.h.  Zeroing the replicas and the cross-rank barrier are the caller's (tp.AllReduceWorkspace)."""
+    prob_m, prob_k = A.size(0), A.size(1)
+    groupsize = -1 if s3.numel() == 0 else prob_k // s3.size(0)
+    if not A.is_cuda:
+        raise RuntimeError("qqq_gemm_reduce: tensors must be CUDA tensors (qqq_b200 has no CPU path).")
+    if not d_multicast_ptr or d_multicast_ptr % 16:
+        raise RuntimeError("qqq_gemm_reduce: a 16-byte aligned multicast address is required (no NVLS multicast support?).")
+    if workspace.numel() < prob_n // 128 * max_par or C.numel() < 64 * max_par * prob_n:
+        raise RuntimeError("qqq_gemm_reduce: workspace / C too small.")
+    dev = A.get_device()
+    err = _lib.load().qqq_gemm_reduce_sm100a(
+        _ptr(A), _ptr(B), _ptr(C), d_multicast_ptr, _ptr(s1), _ptr(s2), _ptr(s3) if s3.numel() else None,
+        prob_m, prob_n, prob_k, _ptr(workspace), groupsize, dev, torch.cuda.current_stream(dev).cuda_stream, -1, -1, sms,
+        max_par,
+    )
+    if err != 0:
+        raise RuntimeError(f"qqq_gemm_reduce_sm100a failed (rc={err}): {_lib.last_error()}")
+
+
 def dynamic_quant(x: torch.Tensor):
     """Per-token int8 quantisation, bit-identical to the reference's 5 eager ops
     (qlinear_marlin.py:265-268), as ONE kernel.  x fp16 [M,K] -> (int8 [M,K], fp32 [M,1])."""
