@@ -18,15 +18,10 @@ def _ptr(t: torch.Tensor) -> int:
     return t.data_ptr()
 
 
-def qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1, max_par=8):
-    """INT8 x INT4 -> FP16 GEMM.  Same 12 arguments, meaning and errors as the reference `qqq_gemm`
-    (csrc/qqq_gemm.cu:1048-1106):
-
-    A int8 [M,K]; B int32 [K/16, 2N] (reference packing); C int32 [>=64*max_par, N] scratch;
-    D fp16 [M,N] out; s1 fp32 [M,1]; s2 fp32 [1,N]; s3 fp16 [K/g, N] or empty; workspace int32
-    [>= N/128*max_par] zeros.  Raises RuntimeError on the same conditions the reference raises AT_ERROR.
-    N is taken from C.size(1) exactly like the reference (:1063).
-    """
+def check_gemm_args(A, B, C, D, s1, s2, s3, workspace, max_par):
+    """The reference's argument checks (csrc/qqq_gemm.cu:1060-1075, same messages) plus the layout / dtype / device
+    checks it omits (it would read garbage or fault instead).  Returns (prob_m, prob_n, prob_k, groupsize) exactly as
+    the reference derives them: N from C.size(1) (:1063), groupsize from s3 (:1065)."""
     prob_m = A.size(0)
     prob_n = C.size(1)
     prob_k = A.size(1)
@@ -41,9 +36,6 @@ def qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1
         raise RuntimeError(f"s2 dtype must be float32, but got {s2.dtype}.")
     if s3.dtype != torch.float16:
         raise RuntimeError(f"s3 dtype must be float16, but got {s3.dtype}.")
-    # Checks the reference omits (it would read garbage / fault instead): layout, dtype and device.
-    if not A.is_cuda:
-        raise RuntimeError("qqq_gemm: tensors must be CUDA tensors (qqq_b200 has no CPU path).")
     for name, t, dt in (("A", A, torch.int8), ("B", B, torch.int32), ("C", C, torch.int32), ("D", D, torch.float16),
                         ("workspace", workspace, torch.int32)):
         if t.dtype != dt:
@@ -54,6 +46,40 @@ def qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1
             raise RuntimeError(f"{name} is on {t.device}, expected {A.device}.")
     if C.size(0) < 64 * max_par and prob_m > 0:
         raise RuntimeError(f"C must have at least {64 * max_par} rows.")
+    return prob_m, prob_n, prob_k, groupsize
+
+
+def install_as_qqq_cuda() -> None:
+    """Make `from QQQ._CUDA import qqq_gemm` (QQQ/gptq/qlinear/qlinear_marlin.py:22) resolve to this library, so the
+    reference's own `QuantLinear` / `mul` run on the sm_100a kernel unchanged (option B)."""
+    import sys
+    import types
+
+    mod = types.ModuleType("QQQ._CUDA")
+    mod.__doc__ = "qqq_b200 shim for the reference's compiled extension (csrc/pybind.cpp:3-5)"
+
+    def _positional(A, B, C, D, s1, s2, s3, workspace, thread_k, thread_n, sms, max_par, /):
+        # pybind's m.def has no py::arg names: all twelve arguments are required and positional
+        return qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k, thread_n, sms, max_par)
+
+    mod.qqq_gemm = _positional
+    sys.modules["QQQ._CUDA"] = mod
+    if "QQQ" in sys.modules:
+        setattr(sys.modules["QQQ"], "_CUDA", mod)
+
+
+def qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1, max_par=8):
+    """INT8 x INT4 -> FP16 GEMM.  Same 12 arguments, meaning and errors as the reference `qqq_gemm`
+    (csrc/qqq_gemm.cu:1048-1106):
+
+    A int8 [M,K]; B int32 [K/16, 2N] (reference packing); C int32 [>=64*max_par, N] scratch;
+    D fp16 [M,N] out; s1 fp32 [M,1]; s2 fp32 [1,N]; s3 fp16 [K/g, N] or empty; workspace int32
+    [>= N/128*max_par] zeros.  Raises RuntimeError on the same conditions the reference raises AT_ERROR.
+    N is taken from C.size(1) exactly like the reference (:1063).
+    """
+    prob_m, prob_n, prob_k, groupsize = check_gemm_args(A, B, C, D, s1, s2, s3, workspace, max_par)
+    if not A.is_cuda:
+        raise RuntimeError("qqq_gemm: tensors must be CUDA tensors (qqq_b200 has no CPU path).")
     dev = A.get_device()
     stream = torch.cuda.current_stream(dev).cuda_stream
     lib = _lib.load()

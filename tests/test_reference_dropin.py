@@ -1,0 +1,91 @@
+"""Drop-in at the reference's own call site: the REFERENCE's `QuantLinear` (QQQ/gptq/qlinear/qlinear_marlin.py, loaded
+from /root/reference where it lies, never copied) imports `qqq_gemm` from `QQQ._CUDA`; `qqq_b200.ops.install_as_qqq_cuda()`
+puts this library there.  The reference module's pack() and forward() then run unchanged: its forward hands our
+`qqq_gemm` the twelve positional arguments with the reference's own buffers (B, reduce_buffer, s_channel, s_group,
+workspace), which must pass our argument checks and give the oracle's result.
+
+CPU: the launch itself needs a GPU, so the C-ABI call is replaced by the oracle; the argument checks are the product's.
+Skipped where the reference tree is absent (the GPU box)."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qqq_oracle as O
+
+REF = os.environ.get("QQQ_REFERENCE_DIR", "/root/reference")
+REF_FILE = os.path.join(REF, "QQQ/gptq/qlinear/qlinear_marlin.py")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_FILE), reason="reference tree not present")
+
+
+@pytest.fixture
+def reference_module(monkeypatch):
+    from qqq_b200 import ops
+
+    calls = []
+
+    def launch_on_oracle(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1, max_par=8):
+        m, n, k, gs = ops.check_gemm_args(A, B, C, D, s1, s2, s3, workspace, max_par)  # the product's checks
+        calls.append((m, n, k, gs, thread_k, thread_n, sms, max_par))
+        D.copy_(torch.from_numpy(O.qqq_gemm_oracle(A.numpy(), B.numpy(), s1.numpy(), s2.numpy(),
+                                                   s3.numpy() if s3.numel() else None)))
+
+    monkeypatch.setattr(ops, "qqq_gemm", launch_on_oracle)
+    monkeypatch.setitem(sys.modules, "QQQ", types.ModuleType("QQQ"))
+    monkeypatch.delitem(sys.modules, "QQQ._CUDA", raising=False)
+    ops.install_as_qqq_cuda()
+    monkeypatch.setattr(torch.cuda, "get_device_capability", lambda *a, **k: (10, 0))
+    spec = importlib.util.spec_from_file_location("ref_qlinear_marlin_dropin", REF_FILE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    yield mod, calls
+    sys.modules.pop("QQQ._CUDA", None)
+
+
+@pytest.mark.parametrize("K,N,gs,M", [(256, 256, -1, 5), (512, 128, 128, 33), (128, 64, -1, 1)])
+def test_reference_quantlinear_runs_on_our_qqq_gemm(reference_module, K, N, gs, M):
+    mod, calls = reference_module
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from gen_pack_golden import fake_quant_problem
+
+    Wfq, scales, s_extra = fake_quant_problem(K, N, gs, seed=K + N)
+    lin = torch.nn.Linear(K, N, bias=True).half()
+    lin.weight.data = Wfq
+    lin.bias.data = torch.linspace(-1, 1, N).half()
+    ref_ql = mod.QuantLinear(4, gs, K, N, bias=True)
+    ref_ql.pack(lin, scales, s_extra)
+    x = (torch.randn(M, K, generator=torch.Generator().manual_seed(3))).half()
+    y = ref_ql(x.reshape(1, M, K))
+    assert y.shape == (1, M, N) and len(calls) == 1
+    assert calls[0] == (M, N, K, gs, -1, -1, -1, 16)  # mul()'s defaults, max_par from the module
+    # expected: oracle on the reference module's own buffers and its own (CPU-evaluated) activation quant
+    A8, s1 = ref_ql.dynamic_quant(x)
+    want = O.qqq_gemm_oracle(A8.numpy(), ref_ql.B.numpy(), s1.numpy(), ref_ql.s_channel.numpy(),
+                             ref_ql.s_group.numpy() if ref_ql.s_group.numel() else None)
+    want = (torch.from_numpy(want) + ref_ql.bias).numpy()
+    assert np.array_equal(y.reshape(M, N).numpy().view(np.uint16), want.view(np.uint16))
+    # and the reference module is interchangeable with ours: same buffers after pack()
+    import qqq_b200
+
+    ours = qqq_b200.QuantLinear(4, gs, K, N, bias=True)
+    ours.pack(lin, scales, s_extra)
+    for name in ("B", "s_channel", "s_group", "bias"):
+        assert torch.equal(getattr(ours, name), getattr(ref_ql, name)), name
+    assert ours.workspace.shape == ref_ql.workspace.shape and ours.reduce_buffer.shape == ref_ql.reduce_buffer.shape
+    sd_ref = {k for k, v in ref_ql.state_dict().items()}
+    sd_ours = {k for k, v in ours.state_dict().items()}
+    assert sd_ref == sd_ours
+
+
+def test_shim_is_positional_only_like_pybind(reference_module):
+    mod, _ = reference_module
+    import QQQ._CUDA as shim  # noqa: N811
+
+    with pytest.raises(TypeError):
+        shim.qqq_gemm(A=None)
+    with pytest.raises(TypeError):
+        shim.qqq_gemm(*([None] * 8))  # the C++ defaults are invisible to Python: all twelve are required
