@@ -39,7 +39,12 @@ SHAPES = [(1, 4096, 4096), (1, 21760, 8192), (16, 21760, 8192), (16, 128, 8192),
           (100, 384, 1152), (128, 21760, 8192), (200, 1024, 1024), (256, 21760, 8192), (300, 640, 768),
           (1000, 384, 512), (1024, 4096, 4096), (1024, 11008, 4096), (1024, 4096, 11008), (1024, 21760, 8192),
           (1024, 2048, 4096), (1024, 1408, 4096), (1100, 256, 256), (4096, 21760, 8192), (4096, 4096, 4096),
-          (5, 128, 64), (7, 320, 1024), (2048, 8192, 1024)]
+          (5, 128, 64), (7, 320, 1024), (2048, 8192, 1024),
+          # the sweep shape transposed (170 k-blocks: last pipeline stage of a tile partly past the end of K)
+          (16, 8192, 21760), (1024, 8192, 21760),
+          # Llama-3-8B decode batch 32 (configs[2]) incl. merged q/k/v and gate/up; Llama-2-70B TP=8 shards (configs[3])
+          (32, 1024, 4096), (32, 6144, 4096), (32, 14336, 4096), (32, 28672, 4096), (32, 4096, 14336),
+          (1024, 128, 8192), (1024, 3584, 8192), (1024, 8192, 3584), (1024, 8192, 1024)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
