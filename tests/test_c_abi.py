@@ -50,14 +50,16 @@ def test_version_and_counters():
 ])
 def test_shape_errors_before_any_cuda_call(n, k, tk, tn, gs, rc):
     lib = _lib.load()
-    got = lib.qqq_gemm_sm100a(None, None, None, None, None, None, None, 4, n, k, None, gs, 0, None, tk, tn, -1, 16)
-    assert got == rc
-    assert len(_lib.last_error()) > 0
+    for entry in (lib.qqq_gemm_sm100a, lib.qqq_gemm_reduce_sm100a):  # the reducing variant shares every check
+        got = entry(None, None, None, None, None, None, None, 4, n, k, None, gs, 0, None, tk, tn, -1, 16)
+        assert got == rc
+        assert len(_lib.last_error()) > 0
 
 
 def test_empty_problem_returns_ok_without_device():
     lib = _lib.load()
     assert lib.qqq_gemm_sm100a(None, None, None, None, None, None, None, 0, 128, 128, None, -1, 0, None, -1, -1, -1, 16) == 0
+    assert lib.qqq_gemm_reduce_sm100a(None, None, None, None, None, None, None, 0, 128, 128, None, -1, 0, None, -1, -1, -1, 16) == 0
     assert lib.qqq_act_quant_sm100a(None, None, None, 0, 128, 0, None) == 0
     assert lib.qqq_act_quant_sm100a(None, None, None, 4, 100, 0, None) == 1
 
