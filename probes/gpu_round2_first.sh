@@ -24,5 +24,14 @@ for gs in (-1,128):
     for M in (64,128,256,512): t.run(M,8192,21760,gs)
 PY
   done
+  # 208-token double-buffered tiles (drain overlapped; 5 x 208 covers 1024) against the default 256-token tiles
+  python probes/build_variant.py probes/libqqq_b200_dbuf208.so -DQQQ_DBUF_MAX_TOK=208 > $O/build_dbuf208.log 2>&1
+  for cfg in "1024 8192 21760 -1" "1024 4096 4096 -1" "1024 4096 11008 -1" "1024 11008 4096 -1" "1024 8192 21760 128" "4096 8192 21760 -1"; do
+    echo "--- default: $cfg" >> $O/time_dbuf208.log
+    timeout 100 python probes/time_ours.py one $cfg >> $O/time_dbuf208.log 2>&1
+    echo "--- dbuf208: $cfg" >> $O/time_dbuf208.log
+    QQQ_B200_NTOK=208 QQQ_B200_LIB=probes/libqqq_b200_dbuf208.so timeout 100 python probes/time_ours.py one $cfg >> $O/time_dbuf208.log 2>&1
+  done
+  QQQ_B200_NTOK=208 QQQ_B200_LIB=probes/libqqq_b200_dbuf208.so timeout 600 python -m pytest tests/test_gemm_parity.py -m gpu -x -q > $O/pytest_dbuf208.log 2>&1; echo "rc=$?" >> $O/pytest_dbuf208.log
 fi
 echo done > $O/done.txt

@@ -310,7 +310,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
       const double t_u = p.ksub * (p.m_tiles == 1 && c_kb < 420.0 ? 420.0 : c_kb);
       const int n_epi = kWarps - kUnpackWarp0 - 4 * p.unpack_groups;
       const double t_d = 730.0 * ((p.n_tok / 16 + n_epi / 4 - 1) / (n_epi / 4)) + 1400.0;
-      const bool dbuf = p.n_tok <= 192;  // double-buffered accumulators: only the last drain of a CTA is exposed
+      const bool dbuf = p.n_tok <= kDbufMaxTok;  // double-buffered accumulators: only the last drain of a CTA is exposed
       const long long waves = (tiles + grid - 1) / grid;
       const double cost_whole = (double)waves * p.k_units * t_u + (dbuf ? 1.0 : (double)waves) * t_d;
       const long long segs = (upc_all + p.k_units - 1) / p.k_units + 1;

@@ -161,7 +161,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int KSUB = p.ksub;                  // 128-deep k sub-blocks per pipeline stage ("unit")
   // TMEM columns: accumulator buffers first (two when they leave >= 128 columns for the weight ring, so the drain of
   // one tile overlaps the MMAs of the next), then the ring of unpacked weight tiles (one slot = one unit = 32*KSUB columns)
-  const int ndbuf = p.n_tok <= 192 ? 2 : 1;
+  const int ndbuf = p.n_tok <= kDbufMaxTok ? 2 : 1;
   const int tmem_a0 = ndbuf * p.n_tok;
   const int NA = min(kMaxASlots, (512 - tmem_a0) / (32 * KSUB));
   // CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent 128-channel tiles of the same token tile

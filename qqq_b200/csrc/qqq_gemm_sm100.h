@@ -15,6 +15,13 @@ constexpr int kStageS = 256;     // group-scale bytes per sub-block: 128 channel
 constexpr int kMaxASlots = 8;    // ring slots of 32*ksub columns each
 constexpr int kMaxStages = 16;
 constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
+// Token tiles up to this size get two accumulator buffers in TMEM (the drain of one tile overlaps the MMAs of the
+// next); the rest of the 512 columns is the unpacked-weight ring.  192 leaves 4 slots of 32 columns; an experiment
+// build with -DQQQ_DBUF_MAX_TOK=208 (3 slots; 5 x 208 tokens cover M = 1024) goes with QQQ_B200_NTOK=208.
+#ifndef QQQ_DBUF_MAX_TOK
+#define QQQ_DBUF_MAX_TOK 192
+#endif
+constexpr int kDbufMaxTok = QQQ_DBUF_MAX_TOK;
 constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr int kStageD = 1024;          // one epilogue staging tile: 16 tokens x 32 channels fp16 (one warp's chunk)
 constexpr int kEpiStageBytes = 8 * kStageD;  // up to 8 epilogue warps
