@@ -1,0 +1,78 @@
+"""Run bench.py's main() on a machine without a GPU (test infrastructure, used by tests/test_bench_hostlogic.py).
+
+The two C-ABI entry points are replaced by the CPU oracle and the small CUDA surface bench.py touches (events, streams,
+graphs, pinned memory) by inert stand-ins; the model is shrunk to 2 tiny layers.  What this exercises is the host logic of
+bench.py: argument handling, the call chains, the guarded auxiliary sections and the JSON contract.  Timings printed by
+such a run mean nothing."""
+import sys, os, types, time, contextlib
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch, numpy as np
+from oracle import qqq_oracle as O
+from qqq_b200 import ops
+import qqq_b200
+cnt = {"c": 0}
+def dq(x):
+    cnt["c"] += 1
+    q, s = O.dynamic_quant(x.detach().contiguous().numpy(), cuda_semantics=True); return torch.from_numpy(q), torch.from_numpy(s)
+def gemm(A,B,C,D,s1,s2,s3,ws,*a,**k):
+    cnt["c"] += 1
+    D.copy_(torch.from_numpy(O.qqq_gemm_oracle(A.numpy(),B.numpy(),s1.numpy(),s2.numpy(),s3.numpy() if s3.numel() else None)))
+ops.dynamic_quant = dq; ops.qqq_gemm = gemm; qqq_b200.qqq_gemm = gemm
+qqq_b200.launch_count = lambda: cnt["c"]
+# --- fake CUDA surface ---
+class Ev:
+    def __init__(s, enable_timing=True): s.t = 0
+    def record(s): s.t = time.perf_counter()
+    def elapsed_time(s, o): return (o.t - s.t) * 1e3 + 1e-3
+class G:
+    def replay(s): s.fn and s.fn()
+class Strm:
+    def wait_stream(s, o): pass
+torch.cuda.is_available = lambda: True
+torch.cuda.set_device = lambda d: None
+torch.cuda.synchronize = lambda *a: None
+torch.cuda.Event = Ev
+torch.cuda.Stream = lambda device=None: Strm()
+torch.cuda.current_stream = lambda d=None: Strm()
+torch.cuda.stream = lambda s: contextlib.nullcontext()
+torch.cuda.get_device_capability = lambda *a: (10, 0)
+torch.Tensor.pin_memory = lambda self: self
+class FakeGraph:
+    def __init__(s): s.fn=None
+    def replay(s): s.fn()
+class fakegraphctx:
+    def __init__(s, g, pool=None): s.g=g
+    def __enter__(s): return s
+    def __exit__(s,*a): pass
+torch.cuda.CUDAGraph = FakeGraph
+torch.cuda.graph = fakegraphctx
+# graph capture: run fn eagerly at capture and at every replay
+import qqq_b200.graph as qg
+class GC:
+    def __init__(s, fn, x, warmup=2, pool=None): s.fn, s.x = fn, x.clone(); s.out = fn(s.x)
+    def __call__(s, x=None):
+        if x is not None: s.x.copy_(x)
+        s.out = s.fn(s.x); return s.out
+qg.GraphedCallable = GC
+qg.capture = lambda fn, x, warmup=2: GC(fn, x)
+src = open(os.path.join(ROOT, "bench.py")).read()
+src = src.replace('dev = f"cuda:{local_rank}"', 'dev = "cpu"')
+src = src.replace('dist.init_process_group("nccl", device_id=torch.device(dev))', 'dist.init_process_group("gloo")')
+src = src.replace('ROOT = os.path.dirname(os.path.abspath(__file__))', 'ROOT = %r' % ROOT)
+mod = types.ModuleType("bench_emu"); mod.__file__ = os.path.join(ROOT, "bench.py")
+exec(compile(src, "bench.py", "exec"), mod.__dict__)
+
+mod.MODEL.update(layers=2, hidden=256, inter=512, seq=16, batch=1)
+mod.LLAMA3_8B.update(layers=2, hidden=256, inter=512, kv=128, batch=4)
+def _gtu(launch_all, n_launches, reps=3, warm=1):
+    launch_all(); return 1.0
+mod.graph_time_us = _gtu
+_orig_sweep = mod.gemm_sweep
+mod.gemm_sweep = lambda dev, peaks, quick=False, K=8192, N=21760, Ms=None: _orig_sweep(dev, peaks, quick, 256 if K == 8192 else 512, 256, (1, 16))
+if "--break-sweep" in sys.argv:  # an auxiliary section that raises must be reported, not propagated
+    sys.argv.remove("--break-sweep")
+    mod.gemm_sweep = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("injected failure"))
+sys.argv = ["bench.py", "--steps", "1", "--warmup", "1"] + sys.argv[1:]
+rc = mod.main()
+print("rc", rc)

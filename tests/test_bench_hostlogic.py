@@ -1,0 +1,89 @@
+"""bench.py's host logic on a CPU-only machine: main() runs end to end on a mocked CUDA surface with the oracle behind
+the C ABI (tests/helpers/bench_on_mock_cuda.py) and must print ONE JSON line that honours the driver's contract —
+including when an auxiliary section fails."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HELPER = os.path.join(ROOT, "tests", "helpers", "bench_on_mock_cuda.py")
+
+
+def _run(*extra):
+    out = subprocess.run([sys.executable, HELPER, *extra], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, "bench.py must print exactly one JSON line"
+    return json.loads(lines[0])
+
+
+@pytest.fixture(scope="module")
+def line():
+    return _run()
+
+
+def test_contract_keys(line):
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 1 and line["higher_is_better"] is True
+    assert line["vs_baseline"] is None and line["data"] == "synthetic" and "workload" in line["config"]
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_launch_accounting_matches_the_call_structure(line):
+    # 2 tiny layers x 7 linears x (activation quant + GEMM); the cache variant quantises shared inputs once
+    assert line["gpu_launches_per_step"] == 28 and line["gpu_launches"] == 28 * line["steps"]
+    assert line["shared_act_quant"]["gpu_launches_per_step"] == 14 + 8
+
+
+def test_auxiliary_sections_present(line):
+    assert isinstance(line["gemm_sweep"], list) and {r["mode"] for r in line["gemm_sweep"]} == {"per-channel", "g128"}
+    assert isinstance(line["gemm_sweep_transposed"], list)
+    assert line["decode_g128"]["unit"] == "tokens/s" and "merged" in line["decode_g128"]
+    assert line["merged"]["value"] > 0
+
+
+def test_a_failing_auxiliary_section_does_not_cost_the_line():
+    line = _run("--break-sweep")
+    assert "error" in line["gemm_sweep"] and "error" in line["gemm_sweep_transposed"]
+    assert line["value"] > 0 and "decode_g128" in line and "cpu_baseline" in line
+
+
+def test_flags_skip_sections():
+    line = _run("--no-sweep", "--no-cpu", "--no-merged", "--no-decode")
+    for k in ("gemm_sweep", "gemm_sweep_transposed", "cpu_baseline", "decode_g128", "shared_act_quant"):
+        assert k not in line
+    assert line["merged"] is None
+
+
+def _torchrun(script, *args, nproc=2, port=29541):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), script, *args]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [json.loads(ln) for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_two_ranks_tensor_parallel_prints_one_line_from_rank0():
+    """The driver's N > 1 launch (torchrun, one rank per GPU): gloo stands in for NCCL, shards come from tp.split_sizes."""
+    lines = _torchrun(HELPER, "--gpus", "2")
+    assert len(lines) == 1
+    line = lines[0]
+    assert line["n_gpus"] == 2 and line["config"]["parallelism"] == "tp2" and line["scaling"] == "strong"
+    assert line["gpu_launches_per_step"] == 28  # per rank: every linear still runs, on its shard
+    assert "gemm_sweep" not in line and "cpu_baseline" not in line  # rank 0 at N = 1 only
+
+
+def test_reference_arm_under_torchrun_only_rank0_speaks():
+    lines = _torchrun(os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+                      port=29543)
+    assert len(lines) == 1 and lines[0]["impl"] == "reference"
+    assert lines[0]["e2e"]["h2d_bytes_per_step"] == 0 and lines[0]["cpu_baseline"]["kind"] == "port"
