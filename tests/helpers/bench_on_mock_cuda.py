@@ -70,6 +70,33 @@ def _gtu(launch_all, n_launches, reps=3, warm=1):
 mod.graph_time_us = _gtu
 _orig_sweep = mod.gemm_sweep
 mod.gemm_sweep = lambda dev, peaks, quick=False, K=8192, N=21760, Ms=None: _orig_sweep(dev, peaks, quick, 256 if K == 8192 else 512, 256, (1, 16))
+if "--fused-allreduce" in sys.argv:
+    # NVLS multicast emulated over gloo: every rank's partial output is added into every rank's replica
+    import torch.distributed as dist
+    from qqq_b200 import tp
+
+    class _Emu:
+        by_addr = {}
+
+        def __init__(self, group=None):
+            pass
+
+        def alloc(self, numel, device):
+            t = torch.full((numel,), 555.0, dtype=torch.float16)
+            addr = 4096 * (len(_Emu.by_addr) + 1)
+            _Emu.by_addr[addr] = t
+            return t, addr, (lambda: dist.barrier())
+
+    def _gemm_reduce(A, B, C, mc, s1, s2, s3, workspace, prob_n, max_par=16, sms=-1):
+        cnt["c"] += 1
+        part = torch.from_numpy(O.qqq_gemm_oracle(A.numpy(), B.numpy(), s1.numpy(), s2.numpy(),
+                                                  s3.numpy() if s3.numel() else None)).float()
+        dist.all_reduce(part)
+        view = _Emu.by_addr[mc][: part.numel()].view(part.shape)
+        view += part.half()
+
+    tp._SymmMemBackend = _Emu
+    ops.qqq_gemm_reduce = _gemm_reduce
 if "--break-sweep" in sys.argv:  # an auxiliary section that raises must be reported, not propagated
     sys.argv.remove("--break-sweep")
     mod.gemm_sweep = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("injected failure"))

@@ -87,3 +87,12 @@ def test_reference_arm_under_torchrun_only_rank0_speaks():
                       port=29543)
     assert len(lines) == 1 and lines[0]["impl"] == "reference"
     assert lines[0]["e2e"]["h2d_bytes_per_step"] == 0 and lines[0]["cpu_baseline"]["kind"] == "port"
+
+
+def test_two_ranks_with_the_all_reduce_fused_into_the_gemm():
+    """--fused-allreduce wiring (row-parallel linears reduce in their own epilogue; multicast emulated over gloo): same
+    launch count, no NCCL all-reduce in the chain, and the same numbers as the unfused run up to fp16 summation order."""
+    fused = _torchrun(HELPER, "--gpus", "2", "--fused-allreduce", port=29547)
+    assert len(fused) == 1
+    assert "fused into the GEMM epilogue" in fused[0]["config"]["parallelism"]
+    assert fused[0]["gpu_launches_per_step"] == 28 and fused[0]["merged"]["value"] > 0
