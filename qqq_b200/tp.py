@@ -129,46 +129,45 @@ class _SymmMemBackend:
 
 
 class AllReduceWorkspace:
-    """Three replicated fp16 buffers shared by every fused row-parallel layer of a model.
+    """Replicated fp16 output buffers shared by every fused row-parallel layer of a model.
 
-    Protocol of fused call i on every rank (all ranks issue the same calls in the same order):
-        zero buffer (i+1)%3  ->  GEMM whose epilogue adds into the multicast address of buffer i%3  ->  barrier
-    * buffer i%3 was zeroed during call i-1, before this rank arrived at barrier i-1; peers start call i only after
-      passing barrier i-1, so their adds never meet a stale value or a late memset;
-    * after barrier i every rank's kernel has completed, so every replica of buffer i%3 holds the sum over ranks;
-    * the output of call i (a view of buffer i%3) stays valid until call i+2 begins (which zeroes it for call i+3):
-      long enough for the residual add that follows o_proj while down_proj already runs.  Consumers that need it
-      longer clone it.
+    Protocol of a fused call on every rank (all ranks issue the same calls in the same order):
+        zero my replica of the region  ->  barrier  ->  GEMM whose epilogue adds into the multicast address  ->  barrier
+    * first barrier: no rank's adds can reach a replica before its owner has zeroed it;
+    * second barrier: every rank's kernel has completed, so every replica holds the sum over ranks.
+    The protocol carries no state from one call to the next (the region is zeroed when its size is known, by the call
+    that uses it), so it is safe under CUDA-graph capture and replay whatever the number of calls per graph and
+    whatever the sequence of shapes.  Calls alternate between two buffers only so that an output stays valid while the
+    next fused call runs (o_proj's output feeds the residual add while down_proj is already reducing); it is
+    overwritten by the call after that.  Consumers that need it longer clone it.
     """
 
-    NBUF = 3
+    NBUF = 2
 
     def __init__(self, max_tokens: int, max_features: int, group=None, device=None, backend=None):
         self.capacity = max_tokens * max_features
         self.backend = backend if backend is not None else _SymmMemBackend(group)
-        self.bufs, self.mc, self.barriers, self.dirty = [], [], [], [0] * self.NBUF
+        self.bufs, self.mc, self.barriers = [], [], []
         for _ in range(self.NBUF):
             t, mc, bar = self.backend.alloc(self.capacity, device)
-            t.zero_()
             self.bufs.append(t)
             self.mc.append(mc)
             self.barriers.append(bar)
         self.turn = 0
-        self.barriers[0]()  # every replica is zero before anybody adds
 
     def begin(self, M: int, N: int):
-        """-> (multicast address to reduce into, this rank's [M, N] view of the result)"""
+        """Zero this rank's replica of an [M, N] region and wait until every rank has done so.
+        -> (multicast address to reduce into, this rank's [M, N] view of the result)"""
         n = M * N
         if n > self.capacity:
             raise RuntimeError(f"AllReduceWorkspace: {M} x {N} exceeds the capacity of {self.capacity} elements")
-        cur, nxt = self.turn, (self.turn + 1) % self.NBUF
-        if self.dirty[nxt]:
-            self.bufs[nxt][: self.dirty[nxt]].zero_()
-            self.dirty[nxt] = 0
-        self.dirty[cur] = n
+        cur = self.turn
+        self.bufs[cur][:n].zero_()
+        self.barriers[cur]()
         return self.mc[cur], self.bufs[cur][:n].view(M, N)
 
     def end(self):
+        """Wait until every rank's reducing GEMM has completed."""
         self.barriers[self.turn]()
         self.turn = (self.turn + 1) % self.NBUF
 
@@ -189,8 +188,8 @@ class FusedRowParallelQuantLinear(nn.Module):
         ql = self.shard
         out_shape = x_local.shape[:-1] + (ql.outfeatures,)
         A = x_local.reshape(-1, x_local.shape[-1]).half()
+        mc, out = self.ws.begin(A.shape[0], ql.outfeatures)  # the barrier's wait overlaps nothing useful later: issue it first
         q, s1 = ql.dynamic_quant(A)
-        mc, out = self.ws.begin(A.shape[0], ql.outfeatures)
         ops.qqq_gemm_reduce(q, ql.B, ql.reduce_buffer, mc, s1, ql.s_channel, ql.s_group, ql.workspace, ql.outfeatures,
                             ql.max_par)
         self.ws.end()
