@@ -306,6 +306,28 @@ def fuse_qkv_gate_up(model: nn.Module) -> int:
     return n
 
 
+def share_scratch(model: nn.Module) -> int:
+    """Point every QuantLinear of `model` at ONE split-K scratch and ONE lock array per device instead of its own
+    `reduce_buffer` (64*max_par x N int32 — 5.5 GB summed over Llama-2-7B) and `workspace`.  Safe because launches of one
+    model are ordered on a stream, the kernel touches scratch and locks only after the preceding kernel has completed
+    (griddepcontrol.wait) and returns the locks zeroed.  Each module keeps a [64*max_par, N] VIEW, so `qqq_gemm` still
+    reads N from `C.size(1)` like the reference (csrc/qqq_gemm.cu:1063).  Returns the bytes released."""
+    by_dev = {}
+    for ql in find_layers(model, [QuantLinear]).values():
+        by_dev.setdefault(ql.B.device, []).append(ql)
+    freed = 0
+    for dev, qls in by_dev.items():
+        rows = max(q.max_par * 64 for q in qls)
+        flat = torch.zeros(rows * max(q.outfeatures for q in qls), dtype=torch.int32, device=dev)
+        locks = torch.zeros(max(max(q.outfeatures // 128 * q.max_par, 16) for q in qls), dtype=torch.int32, device=dev)
+        for q in qls:
+            freed += q.reduce_buffer.numel() * 4 + q.workspace.numel() * 4
+            q.reduce_buffer = flat[: q.max_par * 64 * q.outfeatures].view(q.max_par * 64, q.outfeatures)
+            q.workspace = locks
+        freed -= flat.numel() * 4 + locks.numel() * 4
+    return freed
+
+
 def _decoder_layers(model: nn.Module):
     for cand in ("model.layers", "layers", "model.model.layers"):
         try:
@@ -317,5 +339,5 @@ def _decoder_layers(model: nn.Module):
 
 __all__ = ["find_layers", "recurse_setattr", "recurse_getattr", "decoder_linear_names", "make_quant", "rtn_quantize_weight",
            "rtn_quantizers", "pack_model", "quantize_model_rtn", "quantization_config", "quantized_state_dict",
-           "get_model_architecture", "build_quantized_model", "load_quantized_state_dict", "fuse_qkv_gate_up",
+           "get_model_architecture", "build_quantized_model", "load_quantized_state_dict", "fuse_qkv_gate_up", "share_scratch",
            "FusedProjection"]

@@ -246,3 +246,19 @@ def test_act_quant_cache_reuses_the_shared_input_only(oracle_backend, monkeypatc
     calls.clear()
     ql(x), ql(x)
     assert len(calls) == 2
+
+
+def test_share_scratch_keeps_results_and_releases_memory(oracle_backend):
+    m = qmodel.quantize_model_rtn(tiny_model("llama"), 128)
+    ids = torch.randint(0, 128, (1, 5), generator=torch.Generator().manual_seed(9))
+    ref = _logits(m, ids)
+    keys = set(qmodel.quantized_state_dict(m))
+    freed = qmodel.share_scratch(m)
+    qls = list(qmodel.find_layers(m, [qqq_b200.QuantLinear]).values())
+    assert freed > 0
+    assert len({q.workspace.data_ptr() for q in qls}) == 1 and len({q.reduce_buffer.data_ptr() for q in qls}) == 1
+    for q in qls:  # N is still read from C.size(1); the lock array covers the widest layer
+        assert q.reduce_buffer.shape == (q.max_par * 64, q.outfeatures) and q.reduce_buffer.is_contiguous()
+        assert q.workspace.numel() >= q.outfeatures // 128 * q.max_par
+    assert torch.equal(_logits(m, ids), ref)
+    assert set(qmodel.quantized_state_dict(m)) == keys  # scratch stays out of checkpoints

@@ -97,3 +97,18 @@ def test_act_quant_cache_on_gpu_is_bit_identical_and_saves_launches():
     finally:
         qqq_b200.set_act_quant_cache(False)
     assert torch.equal(ref, got)
+
+
+def test_shared_scratch_on_gpu_is_bit_identical():
+    from qqq_b200 import model as qmodel
+
+    m, _ = _quantized_on_gpu("llama", 128)
+    ids = torch.arange(40, device="cuda:0").reshape(1, 40) * 3 % 128
+    ref = _logits(m, ids)
+    assert qmodel.share_scratch(m) > 0
+    got = _logits(m, ids)
+    assert torch.equal(ref, got)
+    import qqq_b200
+
+    for q in qmodel.find_layers(m, [qqq_b200.QuantLinear]).values():
+        assert int(q.workspace.abs().sum()) == 0
