@@ -419,6 +419,55 @@ def decode_g128(dev, peaks, steps, warmup):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# configs[1] as a whole model: stock HF LlamaForCausalLM with its decoder linears swapped for QuantLinear
+# ----------------------------------------------------------------------------------------------------------
+FULL_MODEL = dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                  num_attention_heads=32, num_key_value_heads=32, max_position_embeddings=4096, seq=1024)
+
+
+def full_forward(dev, steps, warmup):
+    """Llama-2-7B prefill (seq 1024, batch 1) through `transformers.LlamaForCausalLM.forward`: embeddings, RMSNorm,
+    rotary, SDPA attention, SwiGLU and lm_head are stock PyTorch (not on the reference's native hot path either), the 224
+    decoder linears are QuantLinear (random packed weights).  Eager launches, no CUDA graph: what a user of the
+    reference's `model(input_ids)` gets.  Reported beside the linears-only headline, with and without q/k/v + gate/up
+    fusion (qqq_b200.model.fuse_qkv_gate_up)."""
+    import transformers
+
+    import qqq_b200
+    from qqq_b200 import model as qm
+
+    kw = {k: v for k, v in FULL_MODEL.items() if k != "seq"}
+    cfg = transformers.LlamaConfig(tie_word_embeddings=False, **kw)
+    m = qm.build_quantized_model(cfg, qm.quantization_config(-1), dtype=torch.float16, device=torch.device(dev)).eval()
+    gen = torch.Generator(device=dev).manual_seed(99)
+    for ql in qm.find_layers(m, [qqq_b200.QuantLinear]).values():
+        ql.B = random_packed(ql.infeatures, ql.outfeatures, gen, dev)
+        ql.s_channel = torch.full((1, ql.outfeatures), 1.0 / (16 * 4.6 * ql.infeatures ** 0.5), dtype=torch.float32, device=dev)
+    qm.share_scratch(m)
+    S = FULL_MODEL["seq"]
+    ids = torch.randint(0, FULL_MODEL["vocab_size"], (1, S), device=dev, generator=gen)
+    none = lambda: None  # noqa: E731
+
+    def step():
+        with torch.no_grad():
+            return m(input_ids=ids, use_cache=False).logits
+
+    l0 = qqq_b200.launch_count()
+    out = step()
+    n_launch = qqq_b200.launch_count() - l0
+    finite = bool(torch.isfinite(out.float()).all().item())
+    ms = timed(step, steps, warmup, none)
+    res = dict(workload="transformers LlamaForCausalLM (llama-2-7b shape, random init) prefill seq=1024 batch=1, decoder "
+                        "linears = QuantLinear per-channel W4A8, everything else stock PyTorch, eager",
+               ms_per_step=round(ms, 4), value=round(S / (ms * 1e-3), 1), unit="tokens/s",
+               qqq_launches_per_step=int(n_launch), logits_finite=finite)
+    qm.fuse_qkv_gate_up(m)
+    ms_f = timed(step, steps, warmup, none)
+    res["fused_qkv_gate_up"] = dict(ms_per_step=round(ms_f, 4), value=round(S / (ms_f * 1e-3), 1))
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -431,6 +480,7 @@ def main():
     ap.add_argument("--fused-allreduce", action="store_true",
                     help="N > 1: row-parallel linears reduce in their own epilogue (tp.FusedRowParallelQuantLinear)")
     ap.add_argument("--no-decode", action="store_true", help="skip the Llama-3-8B g128 decode section (configs[2])")
+    ap.add_argument("--no-full", action="store_true", help="skip the whole-model (HF Llama forward) section")
     ap.add_argument("--aux-budget", type=float, default=600.0, help="seconds the auxiliary sections may take in total")
     args = ap.parse_args()
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
@@ -603,6 +653,8 @@ def main():
         if world == 1 and not args.no_decode:
             aux.append(("decode_g128", lambda: decode_g128(dev, peaks, args.steps, args.warmup)))
 
+        if world == 1 and not args.no_full:
+            aux.append(("full_forward", lambda: full_forward(dev, args.steps, args.warmup)))
         if world == 1 and not args.no_sweep:  # the sweep shape once transposed (K=21760, N=8192); last
             aux.append(("gemm_sweep_transposed", lambda: gemm_sweep(dev, peaks, K=21760, N=8192, Ms=(16, 1024))))
 

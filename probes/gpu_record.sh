@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 timeout 900 python bench.py > $O/bench.json 2> $O/bench.err
 [ -z "$SKIP_REF" ] && timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"qqq_gemm_kernel|act_quant_kernel" --launch-skip 1344 -c 896 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 1 --no-sweep --no-cpu --no-merged --no-decode > $O/bench_under_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"qqq_gemm_kernel|act_quant_kernel" --launch-skip 1344 -c 896 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 1 --no-sweep --no-cpu --no-merged --no-decode --no-full > $O/bench_under_ncu.log 2>&1
 M="dram__bytes_read.sum,dram__bytes_write.sum"
 for cfg in ${NCU_CFGS:-"16 -1 8192 21760" "1024 -1 8192 21760" "16 128 8192 21760" "1024 128 8192 21760" "1024 -1 4096 4096" "1024 -1 4096 11008" "1024 -1 11008 4096"}; do
   set -- $cfg

@@ -28,12 +28,13 @@ class Ev:
 class G:
     def replay(s): s.fn and s.fn()
 class Strm:
+    def __init__(s, device=None, **k): pass
     def wait_stream(s, o): pass
 torch.cuda.is_available = lambda: True
 torch.cuda.set_device = lambda d: None
 torch.cuda.synchronize = lambda *a: None
 torch.cuda.Event = Ev
-torch.cuda.Stream = lambda device=None: Strm()
+torch.cuda.Stream = Strm
 torch.cuda.current_stream = lambda d=None: Strm()
 torch.cuda.stream = lambda s: contextlib.nullcontext()
 torch.cuda.get_device_capability = lambda *a: (10, 0)
@@ -64,6 +65,8 @@ mod = types.ModuleType("bench_emu"); mod.__file__ = os.path.join(ROOT, "bench.py
 exec(compile(src, "bench.py", "exec"), mod.__dict__)
 
 mod.MODEL.update(layers=2, hidden=256, inter=512, seq=16, batch=1)
+mod.FULL_MODEL.update(vocab_size=128, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, max_position_embeddings=64, seq=12)
 mod.LLAMA3_8B.update(layers=2, hidden=256, inter=512, kv=128, batch=4)
 def _gtu(launch_all, n_launches, reps=3, warm=1):
     launch_all(); return 1.0

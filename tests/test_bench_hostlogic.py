@@ -49,6 +49,8 @@ def test_auxiliary_sections_present(line):
     assert isinstance(line["gemm_sweep_transposed"], list)
     assert line["decode_g128"]["unit"] == "tokens/s" and "merged" in line["decode_g128"]
     assert line["merged"]["value"] > 0
+    ff = line["full_forward"]
+    assert ff["qqq_launches_per_step"] == 28 and ff["logits_finite"] is True and ff["fused_qkv_gate_up"]["value"] > 0
 
 
 def test_a_failing_auxiliary_section_does_not_cost_the_line():
@@ -58,8 +60,8 @@ def test_a_failing_auxiliary_section_does_not_cost_the_line():
 
 
 def test_flags_skip_sections():
-    line = _run("--no-sweep", "--no-cpu", "--no-merged", "--no-decode")
-    for k in ("gemm_sweep", "gemm_sweep_transposed", "cpu_baseline", "decode_g128", "shared_act_quant"):
+    line = _run("--no-sweep", "--no-cpu", "--no-merged", "--no-decode", "--no-full")
+    for k in ("gemm_sweep", "gemm_sweep_transposed", "cpu_baseline", "decode_g128", "shared_act_quant", "full_forward"):
         assert k not in line
     assert line["merged"] is None
 
