@@ -14,6 +14,7 @@ if [ "$1" = "tp" ]; then
 else
   timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "rc=$?" >> $O/pytest_gpu.log
   timeout 900 python bench.py > $O/bench.json 2> $O/bench.err
+  QQQ_B200_PAIR=1 timeout 600 python -m pytest tests/test_gemm_parity.py tests/test_qlinear_gpu.py -m gpu -x -q > $O/pytest_pair_forced.log 2>&1; echo "rc=$?" >> $O/pytest_pair_forced.log
   # pair mode where it is still off by policy: single token tile, 64-256 tokens (trace one CTA pair at M=128)
   for p in 0 1; do
     echo "--- pair=$p" >> $O/time_pair_midM.log
