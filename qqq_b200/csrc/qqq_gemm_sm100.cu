@@ -150,6 +150,46 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
   }
 }
 
+#ifdef QQQ_DRAIN_HELPERS
+// Experiment (-DQQQ_DRAIN_HELPERS; not in the default build).  The accumulator drain is latency-bound with two epilogue
+// warps per SM sub-partition (~730 cycles per 16-token chunk and warp against ~210 of issue), and it is exposed once per
+// tile when the accumulator is single-buffered (n_tok > kDbufMaxTok) and once per CTA otherwise.  The unpack warps sit on
+// the same sub-partitions and idle exactly then: a slot of the TMEM weight ring for unit (last unit of segment s) + NA
+// frees at the moment the MMA completes segment s.  So before unpacking that unit, every unpack warp takes its share of
+// the drain of segment s: a quadrant's chunks go round its 4 members (n_epi/4 epilogue warps, then the G unpack warps).
+// Static membership: every unpack warp waits for and arrives on the accumulator barriers of EVERY segment (so that its
+// parity waits stay in step), but converts and stores only where it pays and is simple: whole tiles (no split-K ticket,
+// no partials), in single-buffer mode or for the CTA's last segment.
+//
+// One 16-token chunk of this lane's channel, whole-tile case: TMEM -> fp32 * s2 * s1 -> fp16 -> warp-private smem tile
+// -> 16-byte row stores (same arithmetic and order as the epilogue warps' `process`).
+template <bool kReduce>
+__device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t tmem_chunk, int m0, int mb, int rows,
+                                                   int col0 /* nt*128 + 32q */, bool q_ok, float s2v, unsigned short* stg,
+                                                   int lane) {
+  uint32_t r[16];
+  tmem_ld_32x32b_x16(tmem_chunk, r);
+  float s1v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s1v[i] = (m0 + mb + i < p.M) ? __ldg(p.s1 + m0 + mb + i) : 0.f;
+  tmem_wait_ld();
+  unsigned short* sp = stg + lane;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    sp[i * 32] = __half_as_ushort(__float2half_rn((__int2float_rn((int)r[i]) * s2v) * s1v[i]));
+  __syncwarp();
+  if (q_ok) {
+    const int st_tok = lane >> 2, st_part = lane & 3;
+    const uint4* rp = reinterpret_cast<const uint4*>(stg) + lane;
+    const uint4 v0 = rp[0], v1 = rp[32];
+    __half* dp = p.D + (size_t)(m0 + mb + st_tok) * p.N + (col0 + 8 * st_part);
+    if (mb + st_tok < rows) emit_d<kReduce>(dp, v0);
+    if (mb + st_tok + 8 < rows) emit_d<kReduce>(dp + (size_t)8 * p.N, v1);
+  }
+  __syncwarp();
+}
+#endif
+
 template <bool GROUPED, bool kPair, bool kReduce = false>
 __global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -220,7 +260,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     if (lane < 2) {
       mbar_init(bar_dfull + 8 * lane, 1);
+#ifdef QQQ_DRAIN_HELPERS
+      mbar_init(bar_dempty + 8 * lane, (n_epi + 4 * G) << PAIR);  // the unpack warps arrive too (drain_share)
+#else
       mbar_init(bar_dempty + 8 * lane, n_epi << PAIR);
+#endif
     }
     mbar_fence_init();
     __syncwarp();
@@ -389,7 +433,64 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int turn = 0;  // which group owns the next sub-block
     int itn = 0;
     const int n_units = sched.num_units();
+#ifdef QQQ_DRAIN_HELPERS
+    // this warp's share of the drain of segment sg (see the comment above helper_drain_chunk)
+    unsigned short* stg_h = reinterpret_cast<unsigned short*>(sStage + (n_epi + (warp - kUnpackWarp0)) * kStageD);
+    bool h_dep_waited = false;
+    auto drain_share = [&](int sg) {
+      int tile, kb0, kb1;
+      sched.segment(sg, tile, kb0, kb1);
+      const int dbuf = sg % ndbuf;
+      const uint32_t dph = (sg / ndbuf) & 1;
+      const bool whole = (kb0 == 0 && kb1 == KU);
+      const bool help = whole && (ndbuf == 1 || sg == n_seg - 1);
+      mbar_wait(bar_dfull + 8 * dbuf, dph);  // every phase is observed, helped or not: parity waits stay in step
+      tc_fence_after();
+      if (help) {
+        if (!h_dep_waited) {  // s1 comes from the preceding kernel; D may still be in use by it
+          grid_dependency_wait();
+          h_dep_waited = true;
+        }
+        const int nt = nt_of(tile), mt = tile % p.m_tiles;
+        const int m0 = mt * p.n_tok;
+        const int rows = min(p.n_tok, p.M - m0);
+        const int n = nt * kTileN + 32 * q + lane;
+        const bool q_ok = nt * kTileN + 32 * q < p.N;
+        const float s2v = n < p.N ? __ldg(p.s2 + s2_position(n)) : 0.f;
+        const uint32_t tmem_d = tmem_base + dbuf * p.n_tok + ((uint32_t)(32 * q) << 16);
+        for (int mb = 16 * ((n_epi >> 2) + grp); mb < rows; mb += 64)
+          helper_drain_chunk<kReduce>(p, tmem_d + mb, m0, mb, rows, nt * kTileN + 32 * q, q_ok, s2v, stg_h, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR)
+          mbar_arrive_cluster(lead_dempty + 8 * dbuf);
+        else
+          mbar_arrive(bar_dempty + 8 * dbuf);
+      }
+    };
+    int h_seg = 0, h_end = 0;  // next segment to take a share of; number of units in segments [0, h_seg]
+    if (n_seg > 0) {
+      int t_, a_, b_;
+      sched.segment(0, t_, a_, b_);
+      h_end = b_ - a_;
+    }
+    auto drain_due = [&](int u) {  // segments whose last unit lies NA or more units behind unit u
+      while (h_seg < n_seg && h_end - 1 + NA <= u) {
+        drain_share(h_seg);
+        if (++h_seg < n_seg) {
+          int t_, a_, b_;
+          sched.segment(h_seg, t_, a_, b_);
+          h_end += b_ - a_;
+        }
+      }
+    };
+#endif
     for (int u = 0; u < n_units; ++u) {
+#ifdef QQQ_DRAIN_HELPERS
+      drain_due(u);
+#endif
       bool stage_ready = false, slot_ready = false;
       for (int sub = 0; sub < KSUB; ++sub, ++itn) {
         if (turn == grp) {
@@ -455,6 +556,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       st.advance();
       as.advance();
     }
+#ifdef QQQ_DRAIN_HELPERS
+    drain_due(0x3fffffff);  // the segments still outstanding when the units run out (always: the last one)
+#endif
   } else if (warp >= epi_warp0) {
     // ===================================== epilogue warps ===================================
     const int q = warp & 3;
@@ -588,6 +692,10 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // Software-pipelined drain: the TMEM load of the next chunk is in flight while this one is converted and
       // stored (TMEM reads run at 64 B/clk per SM: 2048 cycles for a 128 x 256 accumulator).
       {
+#ifdef QQQ_DRAIN_HELPERS
+        // helped segments (same rule as drain_share): the quadrant's chunks go round 4 members, epilogue warps first
+        const int mstep = (whole && (ndbuf == 1 || seg == n_seg - 1)) ? 64 : 16 * (n_epi >> 2);
+#endif
         uint32_t ra[16], rb[16];
         int mb = 16 * eh;
         if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);

@@ -24,7 +24,13 @@ constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
 constexpr int kDbufMaxTok = QQQ_DBUF_MAX_TOK;
 constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr int kStageD = 1024;          // one epilogue staging tile: 16 tokens x 32 channels fp16 (one warp's chunk)
+// Experiment build -DQQQ_DRAIN_HELPERS: the unpack warps take a share of the accumulator drain of whole tiles (see
+// drain_share in qqq_gemm_sm100.cu); every unpack / epilogue warp then needs a staging tile.
+#ifdef QQQ_DRAIN_HELPERS
+constexpr int kEpiStageBytes = 16 * kStageD;
+#else
 constexpr int kEpiStageBytes = 8 * kStageD;  // up to 8 epilogue warps
+#endif
 // warp roles: 0 weights TMA, 1 MMA (+TMEM alloc), 2 tokens TMA, 3 idle, then 4*G unpack warps (G groups x 4 TMEM
 // lane quadrants) and the remaining 16-4G warps as epilogue (G = 2: 8 epilogue warps, G = 3: 4).  24 warps
 // (G up to 4) were measured and did not help: all warps of a TMEM quadrant share one SM sub-partition, so extra

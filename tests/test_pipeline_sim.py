@@ -1,0 +1,105 @@
+"""CPU: the kernel's intra-CTA synchronisation protocol on a discrete-event model (tests/pipeline_sim.py) — deadlock
+freedom, parity waits that never pass a phase early or miss one, every accumulator chunk drained exactly once — on the
+schedules the planner really produces, for the default build and for the drain-helper experiment build."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+
+from pipeline_sim import CtaSim, Deadlock, segments
+from test_schedule import KEYS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SHAPES = [  # (M, N, K, groupsize)
+    (1, 4096, 4096, -1), (16, 21760, 8192, -1), (16, 21760, 8192, 128), (32, 14336, 4096, 128), (64, 21760, 8192, -1),
+    (128, 21760, 8192, -1), (128, 21760, 8192, 128), (200, 1024, 1024, -1), (256, 21760, 8192, -1), (300, 640, 768, 128),
+    (1000, 384, 512, -1), (1024, 4096, 4096, -1), (1024, 11008, 4096, -1), (1024, 4096, 11008, 128),
+    (1024, 21760, 8192, -1), (1024, 8192, 21760, 128), (4096, 21760, 8192, -1), (1100, 256, 256, -1), (2048, 8192, 1024, -1),
+]
+
+
+def _plan(lib, M, N, K, gs, sms):
+    out = (ctypes.c_int * 20)()
+    assert lib.qqq_b200_plan(M, N, K, gs, sms, 16, out) == 0
+    return dict(zip(KEYS, out))
+
+
+@pytest.fixture(scope="session")
+def default_lib():
+    from qqq_b200 import _lib
+
+    return _lib.load()
+
+
+@pytest.fixture(scope="session")
+def helpers_lib(tmp_path_factory):
+    """Planner of the -DQQQ_DRAIN_HELPERS experiment build (larger epilogue staging area -> other ring depths)."""
+    out = tmp_path_factory.mktemp("variant") / "libqqq_b200_helpers.so"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "probes", "build_variant.py"), str(out), "-DQQQ_DRAIN_HELPERS"],
+                          stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(str(out))
+    lib.qqq_b200_plan.argtypes = [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_int)]
+    lib.qqq_b200_plan.restype = ctypes.c_int
+    return lib
+
+
+def _ctas(p):
+    n = p["grid"] >> p["pair"]
+    return sorted({0, 1 % n, n // 2, n - 1})
+
+
+def _simulate(lib, M, N, K, gs, sms, helpers, seeds=(0, 1)):
+    p = _plan(lib, M, N, K, gs, sms)
+    for cta in _ctas(p):
+        if not segments(p, cta):
+            continue
+        for seed in seeds:
+            CtaSim(p, cta, M, seed=seed, helpers=helpers, twin=bool(p["pair"])).run()
+
+
+@pytest.mark.parametrize("M,N,K,gs", SHAPES)
+@pytest.mark.parametrize("sms", [148, 37])
+def test_default_kernel_protocol(default_lib, M, N, K, gs, sms):
+    _simulate(default_lib, M, N, K, gs, sms, helpers=False)
+
+
+@pytest.mark.parametrize("M,N,K,gs", SHAPES)
+@pytest.mark.parametrize("sms", [148, 37])
+def test_drain_helper_variant_protocol(helpers_lib, M, N, K, gs, sms):
+    _simulate(helpers_lib, M, N, K, gs, sms, helpers=True)
+
+
+def test_model_catches_the_round1_ring_depth_bug(default_lib):
+    """Weight-ring depth 7 with two unpack groups and one k-block per stage (the configuration of the first kernels): a
+    stage alternates between the groups, so a group waits on a barrier whose previous phase it never observed and passes
+    on stale parity when that load is late.  The model must flag it; with a depth that is a multiple of the ownership
+    period (what the planner guarantees, tests/test_schedule.py) it must not."""
+    p = _plan(default_lib, 1024, 21760, 8192, -1, 148)
+    assert p["ksub"] == 1 and p["unpack_groups"] == 2
+    bad = dict(p, stages_w=7, pair=0)
+    hit = 0
+    for seed in range(40):
+        try:
+            CtaSim(bad, 0, 1024, seed=seed).run()
+        except Deadlock:
+            hit += 1
+        except AssertionError as e:
+            assert "stale parity" in str(e) or "ran ahead" in str(e) or "more arrivals" in str(e)
+            hit += 1
+    assert hit > 0, "the model no longer reproduces the stale-parity race"
+    good = dict(p, stages_w=6, pair=0)
+    for seed in range(10):
+        CtaSim(good, 0, 1024, seed=seed).run()
+
+
+def test_model_catches_a_wrong_arrival_count(default_lib):
+    p = _plan(default_lib, 128, 4096, 4096, -1, 148)
+    sim = CtaSim(p, 0, 128, seed=0)
+    for b in sim.dempty:  # helpers' arrivals expected but nobody sends them
+        b.count = b.pending = b.count + 4 * p["unpack_groups"]
+    if len(segments(p, 0)) > sim.ndbuf:
+        with pytest.raises(Deadlock):
+            sim.run()
