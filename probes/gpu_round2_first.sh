@@ -39,7 +39,7 @@ PY
   python probes/build_variant.py probes/libqqq_b200_helpers.so -DQQQ_DRAIN_HELPERS > $O/build_helpers.log 2>&1
   QQQ_B200_LIB=probes/libqqq_b200_helpers.so timeout 600 python -m pytest tests/test_gemm_parity.py tests/test_qlinear_gpu.py -m gpu -x -q > $O/pytest_helpers.log 2>&1; echo "rc=$?" >> $O/pytest_helpers.log
   for cfg in "1024 8192 21760 -1" "1024 4096 4096 -1" "1024 4096 11008 -1" "1024 11008 4096 -1" "4096 8192 21760 -1" "128 8192 21760 -1" "1024 8192 21760 128"; do
-    for split in "" 0; do
+    for split in -1 0; do   # -1: the planner decides (same as unset); 0: whole tiles only
       echo "--- default split=$split: $cfg" >> $O/time_helpers.log
       QQQ_B200_SPLIT=$split timeout 100 python probes/time_ours.py one $cfg >> $O/time_helpers.log 2>&1
       echo "--- helpers split=$split: $cfg" >> $O/time_helpers.log
