@@ -312,7 +312,13 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
       const double t_d = 730.0 * ((p.n_tok / 16 + n_epi / 4 - 1) / (n_epi / 4)) + 1400.0;
       const bool dbuf = p.n_tok <= kDbufMaxTok;  // double-buffered accumulators: only the last drain of a CTA is exposed
       const long long waves = (tiles + grid - 1) / grid;
-      const double cost_whole = (double)waves * p.k_units * t_u + (dbuf ? 1.0 : (double)waves) * t_d;
+#ifdef QQQ_DRAIN_HELPERS
+      // whole tiles are drained by 4 warps per TMEM quadrant (epilogue + unpack warps), split tiles by the epilogue warps
+      const double t_dw = 730.0 * ((p.n_tok / 16 + 3) / 4) + 1400.0;
+#else
+      const double t_dw = t_d;
+#endif
+      const double cost_whole = (double)waves * p.k_units * t_u + (dbuf ? 1.0 : (double)waves) * t_dw;
       const long long segs = (upc_all + p.k_units - 1) / p.k_units + 1;
       const double cost_split = (double)upc_all * t_u + (dbuf ? 1.0 : (double)segs) * t_d;
       if (env_split == 1 || cost_split < cost_whole) {
