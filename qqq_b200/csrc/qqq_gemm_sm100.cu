@@ -164,15 +164,12 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
 // One 16-token chunk of this lane's channel, whole-tile case: TMEM -> fp32 * s2 * s1 -> fp16 -> warp-private smem tile
 // -> 16-byte row stores (same arithmetic and order as the epilogue warps' `process`).
 template <bool kReduce>
-__device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t tmem_chunk, int m0, int mb, int rows,
+__device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, const uint32_t (&r)[16], int m0, int mb, int rows,
                                                    int col0 /* nt*128 + 32q */, bool q_ok, float s2v, unsigned short* stg,
                                                    int lane) {
-  uint32_t r[16];
-  tmem_ld_32x32b_x16(tmem_chunk, r);
   float s1v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) s1v[i] = (m0 + mb + i < p.M) ? __ldg(p.s1 + m0 + mb + i) : 0.f;
-  tmem_wait_ld();
   unsigned short* sp = stg + lane;
 #pragma unroll
   for (int i = 0; i < 16; ++i)
@@ -458,8 +455,23 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const bool q_ok = nt * kTileN + 32 * q < p.N;
         const float s2v = n < p.N ? __ldg(p.s2 + s2_position(n)) : 0.f;
         const uint32_t tmem_d = tmem_base + dbuf * p.n_tok + ((uint32_t)(32 * q) << 16);
-        for (int mb = 16 * ((n_epi >> 2) + grp); mb < rows; mb += 64)
-          helper_drain_chunk<kReduce>(p, tmem_d + mb, m0, mb, rows, nt * kTileN + 32 * q, q_ok, s2v, stg_h, lane);
+        // software-pipelined like the epilogue warps: the TMEM load of the next chunk is in flight while this one is
+        // converted and stored
+        uint32_t ra[16], rb[16];
+        int mb = 16 * ((n_epi >> 2) + grp);
+        const int col0 = nt * kTileN + 32 * q;
+        if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
+        while (mb < rows) {
+          tmem_wait_ld();
+          const int mb2 = mb + 64;
+          if (mb2 < rows) tmem_ld_32x32b_x16(tmem_d + mb2, rb);
+          helper_drain_chunk<kReduce>(p, ra, m0, mb, rows, col0, q_ok, s2v, stg_h, lane);
+          if (mb2 >= rows) break;
+          tmem_wait_ld();
+          mb = mb2 + 64;
+          if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
+          helper_drain_chunk<kReduce>(p, rb, m0, mb2, rows, col0, q_ok, s2v, stg_h, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
