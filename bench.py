@@ -606,6 +606,7 @@ def main():
                     peak_source=f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['source']}); int8 dense = 2x bf16 "
                                 "on sm_100a; UTCIMMA-only microbenchmark on this pool measured 4428 TOP/s burst "
                                 "(profiles/r01/probe_umma_i8.log)",
+                    frac_of_burst_umma_i8_peak=round(achieved / 4428.0, 4),  # the stricter, clock-unthrottled denominator
                     launches=n_gemm, avg_launch_us=round(ms_gemm * 1e3 / n_gemm, 2),
                     algorithmic_flops_per_step=flops_rank, algorithmic_bytes_per_step=model_gemm_bytes(M) / world)
 
