@@ -12,8 +12,10 @@ latencies and warp interleavings, and checks what a GPU run can only show as a h
   * every 16-token chunk of every accumulator is drained exactly once, also with the drain-helper variant
     (-DQQQ_DRAIN_HELPERS: unpack warps take a share of the drain, see drain_share in the kernel).
 
-Cross-CTA split-K waits are not modelled (publishers never wait, so they cannot close a cycle); CTA pairs are modelled as
-this CTA's view with the doubled arrival counts supplied by an identical twin.
+Cross-CTA split-K waits are not modelled (publishers never wait, so they cannot close a cycle).  CTA pairs
+(cta_group::2): `PairSim` runs both CTAs on one clock — own weight rings, unpack and epilogue warps, half of the token
+tile each; the leader's MMA warp waits on barriers that collect both CTAs' arrivals and its commits are multicast to
+both (`twin=True` is the cheaper approximation: one CTA with doubled arrival counts).
 """
 from __future__ import annotations
 
@@ -70,8 +72,11 @@ class Deadlock(AssertionError):
 
 
 class CtaSim:
-    def __init__(self, plan, cta, M, seed=0, helpers=False, dbuf_max_tok=192, twin=False):
-        self.p, self.rng, self.helpers = plan, random.Random(seed), helpers
+    def __init__(self, plan, cta, M, seed=0, helpers=False, dbuf_max_tok=192, twin=False, leader=None):
+        """twin=True: CTA pair approximated by doubling this CTA's arrivals on the shared barriers.
+        leader=<CtaSim>: this object is the PEER CTA (rank 1) of a faithfully modelled pair (see PairSim)."""
+        self.p, self.rng, self.helpers = plan, (leader.rng if leader else random.Random(seed)), helpers
+        self.leader = leader
         self.segs = segments(plan, cta)
         self.KU, self.KSUB, self.G = plan["k_units"], plan["ksub"], plan["unpack_groups"]
         self.NSW, self.NST = plan["stages_w"], plan["stages_t"]
@@ -87,15 +92,29 @@ class CtaSim:
         self.afull, self.aempty = mk("afull", K_MAX_A_SLOTS, 4 * self.KSUB * self.pair), mk("aempty", K_MAX_A_SLOTS, 1)
         n_dempty = (self.n_epi + (4 * self.G if helpers else 0)) * self.pair
         self.dfull, self.dempty = mk("dfull", 2, 1), mk("dempty", 2, n_dempty)
-        self.time, self.events = 0, []  # (due, seq, fn): asynchronous completions (TMA landed, MMA retired)
-        self.seq = 0
+        self.clock = leader.clock if leader else {"t": 0, "seq": 0, "events": []}  # shared by the CTAs of a pair
+        self.peer = None
+        if leader is not None:
+            # cta_group::2: the leader's MMA warp waits on ITS token-full / weights-unpacked / accumulator-empty barriers,
+            # which collect both CTAs' arrivals; commits are multicast to the per-CTA barriers of both
+            leader.peer = self
+            leader.fullt = [MBar(f"fullt[{i}]", 2) for i in range(self.NST)]  # model: one arrival per CTA's TMA
+            for b in leader.afull:
+                b.count = b.pending = 4 * self.KSUB * 2
+            for b in leader.dempty:
+                b.count = b.pending = (self.n_epi + (4 * self.G if helpers else 0)) * 2
+            self.fullt, self.afull, self.dempty = leader.fullt, leader.afull, leader.dempty
         self.drained = {}  # (segment, quadrant, chunk) -> count
         self.units = [(sg, kb) for sg, (_, kb0, kb1) in enumerate(self.segs) for kb in range(kb0, kb1)]
 
     # ---- asynchronous engines ---------------------------------------------------------------------------------
+    @property
+    def time(self):
+        return self.clock["t"]
+
     def later(self, lo, hi, fn):
-        self.seq += 1
-        self.events.append((self.time + self.rng.randint(lo, hi), self.seq, fn))
+        self.clock["seq"] += 1
+        self.clock["events"].append((self.time + self.rng.randint(lo, hi), self.clock["seq"], fn))
 
     def arrive_twice_if_pair(self, bar):
         bar.arrive(self.pair)  # the twin CTA does the same thing at (in the model) the same moment
@@ -133,8 +152,11 @@ class CtaSim:
                 due = max(last_retire[0], self.time) + self.rng.randint(100, 600)
                 last_retire[0] = due
                 bars = [self.aempty[as_.idx], self.emptyt[st.idx]] + ([self.dfull[dbuf]] if kb == kb1 - 1 else [])
-                self.seq += 1
-                self.events.append((due, self.seq, lambda bars=bars: [b.arrive() for b in bars]))
+                if self.peer is not None:  # tcgen05.commit.multicast::cluster: the same barriers in the peer CTA
+                    bars += [self.peer.aempty[as_.idx], self.peer.emptyt[st.idx]] + (
+                        [self.peer.dfull[dbuf]] if kb == kb1 - 1 else [])
+                self.clock["seq"] += 1
+                self.clock["events"].append((due, self.clock["seq"], lambda bars=bars: [b.arrive() for b in bars]))
                 yield ("sleep", self.rng.randint(20, 200))
                 st.advance()
                 as_.advance()
@@ -205,26 +227,35 @@ class CtaSim:
             self.dempty[dbuf].arrive(self.pair)
 
     # ---- scheduler ------------------------------------------------------------------------------------------------
-    def run(self):
-        roles = {"W": self.weights_producer(), "T": self.tokens_producer(), "M": self.mma_issuer()}
+    def roles(self, tag=""):
+        roles = {tag + "W": self.weights_producer(), tag + "T": self.tokens_producer()}
+        if self.leader is None:
+            roles[tag + "M"] = self.mma_issuer()  # pair: the leader CTA only
         for g in range(self.G):
             for q in range(4):
-                roles[f"U{g}.{q}"] = self.unpack_warp(g, q)
+                roles[f"{tag}U{g}.{q}"] = self.unpack_warp(g, q)
         for e in range(self.n_epi):
-            roles[f"E{e}"] = self.epilogue_warp(e)
+            roles[f"{tag}E{e}"] = self.epilogue_warp(e)
+        return roles
+
+    def run(self, extra_roles=None):
+        roles = self.roles()
+        if extra_roles:
+            roles.update(extra_roles)
+        clock = self.clock
         state = {k: ("ready", None) for k in roles}  # ready | ("wait", bar, parity, phase) | ("sleep", until)
         done = set()
         while len(done) < len(roles):
             # fire asynchronous completions that are due
-            self.events.sort()
-            while self.events and self.events[0][0] <= self.time:
-                self.events.pop(0)[2]()
+            clock["events"].sort()
+            while clock["events"] and clock["events"][0][0] <= clock["t"]:
+                clock["events"].pop(0)[2]()
             progressed = False
             names = [k for k in roles if k not in done]
             self.rng.shuffle(names)
             for k in names:
                 kind, arg = state[k]
-                if kind == "sleep" and arg > self.time:
+                if kind == "sleep" and arg > clock["t"]:
                     continue
                 if kind == "wait":
                     bar, parity, phase = arg
@@ -241,19 +272,32 @@ class CtaSim:
                     continue
                 progressed = True
                 if ev[0] == "sleep":
-                    state[k] = ("sleep", self.time + ev[1])
+                    state[k] = ("sleep", clock["t"] + ev[1])
                 else:
                     state[k] = ("wait", ev[1:])
             if not progressed:
                 sleepers = [state[k][1] for k in names if state[k][0] == "sleep"]
-                nxt = min(sleepers + [e[0] for e in self.events], default=None)
+                nxt = min(sleepers + [e[0] for e in clock["events"]], default=None)
                 if nxt is None:
                     blocked = {k: (state[k][1][0].name, state[k][1][2]) for k in names if state[k][0] == "wait"}
-                    raise Deadlock(f"deadlock at t={self.time}: {blocked}")
-                self.time = max(self.time + 1, nxt)
+                    raise Deadlock(f"deadlock at t={clock['t']}: {blocked}")
+                clock["t"] = max(clock["t"] + 1, nxt)
+        self.check_drained()
+        if self.peer is not None:
+            self.peer.check_drained()
+        return clock["t"]
+
+    def check_drained(self):
         # every chunk of every segment exactly once per quadrant
         for sg in range(len(self.segs)):
             for q in range(4):
                 for c in range(-(-self.seg_rows(sg) // 16)):
                     assert self.drained.get((sg, q, c), 0) == 1, f"segment {sg} quadrant {q} chunk {c}: drained {self.drained.get((sg, q, c), 0)}x"
-        return self.time
+
+
+def PairSim(plan, cta, M, seed=0, helpers=False, dbuf_max_tok=192):
+    """Both CTAs of a pair (cluster of 2, cta_group::2) on one clock: each has its own weight ring and unpack / epilogue
+    warps and loads half of the token tile; the leader's MMA warp consumes both and its commits release both."""
+    lead = CtaSim(plan, cta, M, seed=seed, helpers=helpers, dbuf_max_tok=dbuf_max_tok)
+    peer = CtaSim(plan, cta, M, seed=seed, helpers=helpers, dbuf_max_tok=dbuf_max_tok, leader=lead)
+    return lead.run(extra_roles=peer.roles("peer:"))

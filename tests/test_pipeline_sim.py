@@ -8,7 +8,7 @@ import sys
 
 import pytest
 
-from pipeline_sim import CtaSim, Deadlock, segments
+from pipeline_sim import CtaSim, Deadlock, PairSim, segments
 from test_schedule import KEYS
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -53,11 +53,16 @@ def _ctas(p):
 
 def _simulate(lib, M, N, K, gs, sms, helpers, seeds=(0, 1)):
     p = _plan(lib, M, N, K, gs, sms)
+    if sms != 148 or p["pair"]:
+        seeds = seeds[:1]  # keep the CPU suite short; probes/sim_stress_helpers.py is the long run
     for cta in _ctas(p):
         if not segments(p, cta):
             continue
         for seed in seeds:
-            CtaSim(p, cta, M, seed=seed, helpers=helpers, twin=bool(p["pair"])).run()
+            if p["pair"]:
+                PairSim(p, cta, M, seed=seed, helpers=helpers)
+            else:
+                CtaSim(p, cta, M, seed=seed, helpers=helpers).run()
 
 
 @pytest.mark.parametrize("M,N,K,gs", SHAPES)
@@ -103,3 +108,26 @@ def test_model_catches_a_wrong_arrival_count(default_lib):
     if len(segments(p, 0)) > sim.ndbuf:
         with pytest.raises(Deadlock):
             sim.run()
+
+
+@pytest.mark.parametrize("M,N,K,gs", [(1024, 21760, 8192, -1), (4096, 21760, 8192, 128), (4096, 4096, 4096, -1)])
+def test_cta_pair_protocol_both_ctas(default_lib, M, N, K, gs, monkeypatch):
+    """Shapes where the planner's policy turns pairs on: both CTAs of a pair on one clock."""
+    p = _plan(default_lib, M, N, K, gs, 148)
+    assert p["pair"] == 1
+    for cta in _ctas(p):
+        for seed in range(2):
+            PairSim(p, cta, M, seed=seed)
+
+
+def test_pair_model_catches_a_missing_multicast(default_lib):
+    """If the leader's commit did not reach the peer's barriers the peer's producers would starve: the model must see it."""
+    import pipeline_sim
+
+    p = _plan(default_lib, 1024, 21760, 8192, -1, 148)
+    lead = CtaSim(p, 0, 1024, seed=0)
+    peer = CtaSim(p, 0, 1024, seed=0, leader=lead)
+    lead.peer = None  # commits stay local
+    with pytest.raises((Deadlock, AssertionError)):
+        lead.run(extra_roles=peer.roles("peer:"))
+    assert pipeline_sim.PairSim(p, 0, 1024, seed=1) > 0
