@@ -164,9 +164,16 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
 // One 16-token chunk of this lane's channel, whole-tile case: TMEM -> fp32 * s2 * s1 -> fp16 -> warp-private smem tile
 // -> 16-byte row stores (same arithmetic and order as the epilogue warps' `process`).
 template <bool kReduce>
-__device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, const uint32_t (&r)[16], int m0, int mb, int rows,
+__device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t (&r)[16], int m0, int mb, int rows,
                                                    int col0 /* nt*128 + 32q */, bool q_ok, float s2v, unsigned short* stg,
-                                                   int lane) {
+                                                   int lane, const int* __restrict__ partials, int others,
+                                                   size_t ticket_stride) {
+  // finisher of a split tile: add the partial tiles the other contributors published (block layout as in `process`)
+  for (int pp = 0; pp < others; ++pp) {
+    const int* __restrict__ src = partials + (size_t)pp * ticket_stride + (size_t)mb * kTileN;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] += (uint32_t)__ldcg(src + i * kTileN);
+  }
   float s1v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) s1v[i] = (m0 + mb + i < p.M) ? __ldg(p.s1 + m0 + mb + i) : 0.f;
@@ -263,6 +270,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_init(bar_dempty + 8 * lane, n_epi << PAIR);
 #endif
     }
+#ifdef QQQ_DRAIN_HELPERS
+    if (lane == 0) misc[2] = misc[3] = 0;  // split-K ticket hand-off to the unpack warps, one word per accumulator buffer
+#endif
     mbar_fence_init();
     __syncwarp();
   }
@@ -440,9 +450,26 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int dbuf = sg % ndbuf;
       const uint32_t dph = (sg / ndbuf) & 1;
       const bool whole = (kb0 == 0 && kb1 == KU);
-      const bool help = whole && (ndbuf == 1 || sg == n_seg - 1);
+      const bool where = ndbuf == 1 || sg == n_seg - 1;  // single-buffer mode, or the CTA's last (always exposed) drain
       mbar_wait(bar_dfull + 8 * dbuf, dph);  // every phase is observed, helped or not: parity waits stay in step
       tc_fence_after();
+      // split tile: the epilogue takes the ticket (and, as finisher, waits for the published partials) and hands the
+      // result over through misc[2 + dbuf] = (segment + 1) << 16 | ticket
+      const int parts = whole ? 1 : (tile * KU + KU - 1) / p.a_upc - (tile * KU) / p.a_upc + 1;
+      int ticket = 0;
+      if (!whole) {
+        uint32_t v = 0;
+        if (lane == 0) {
+          volatile uint32_t* hinfo = misc + 2 + dbuf;
+          while (((v = *hinfo) >> 16) != (uint32_t)(sg + 1)) {
+          }
+        }
+        v = __shfl_sync(0xffffffffu, v, 0);
+        ticket = (int)(v & 0xFFFFu);
+        __threadfence();  // reads of the published partials come after the epilogue's acquire
+      }
+      const bool finish = whole || ticket == parts - 1;
+      const bool help = where && finish;  // publishers' partial stores stay with the epilogue warps (they announce them)
       if (help) {
         if (!h_dep_waited) {  // s1 comes from the preceding kernel; D may still be in use by it
           grid_dependency_wait();
@@ -455,6 +482,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const bool q_ok = nt * kTileN + 32 * q < p.N;
         const float s2v = n < p.N ? __ldg(p.s2 + s2_position(n)) : 0.f;
         const uint32_t tmem_d = tmem_base + dbuf * p.n_tok + ((uint32_t)(32 * q) << 16);
+        const size_t tile_ints = (size_t)p.n_tok * kTileN;
+        const int rtile = (tile << PAIR) + (int)rank;
+        const int* __restrict__ cbase = p.C + (size_t)rtile * tile_ints + 32 * q + lane;
+        const size_t ticket_stride = (size_t)(p.a_tiles << PAIR) * tile_ints;
+        const int others = whole ? 0 : parts - 1;
         // software-pipelined like the epilogue warps: the TMEM load of the next chunk is in flight while this one is
         // converted and stored
         uint32_t ra[16], rb[16];
@@ -465,12 +497,12 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           tmem_wait_ld();
           const int mb2 = mb + 64;
           if (mb2 < rows) tmem_ld_32x32b_x16(tmem_d + mb2, rb);
-          helper_drain_chunk<kReduce>(p, ra, m0, mb, rows, col0, q_ok, s2v, stg_h, lane);
+          helper_drain_chunk<kReduce>(p, ra, m0, mb, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
           if (mb2 >= rows) break;
           tmem_wait_ld();
           mb = mb2 + 64;
           if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
-          helper_drain_chunk<kReduce>(p, rb, m0, mb2, rows, col0, q_ok, s2v, stg_h, lane);
+          helper_drain_chunk<kReduce>(p, rb, m0, mb2, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
         }
       }
       tc_fence_before();
@@ -576,7 +608,11 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int q = warp & 3;
     const int epi_tid = threadIdx.x - epi_warp0 * 32;
     const int eh = (warp - epi_warp0) >> 2;  // which of the n_epi/4 warps of this quadrant: takes every (n_epi/4)-th chunk
+#ifdef QQQ_DRAIN_HELPERS
+    int mstep = 16 * (n_epi >> 2);  // per segment: 64 where the unpack warps take their share (see drain_share)
+#else
     const int mstep = 16 * (n_epi >> 2);
+#endif
     // D leaves through a warp-private shared-memory tile: the warp holds a chunk as [channel = lane][16 tokens]; it
     // writes it as [16 tokens][32 channels] fp16 (row = 64 B, conflict-free), then every lane re-reads 16 B = 8
     // channels of one token and stores them: 2 vector stores per lane and chunk (each instruction covers 8 token
@@ -645,8 +681,17 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           named_bar_sync(1, n_epi_thr);
           __threadfence();  // order this thread's reads of the published partials after the acquire above
         }
+#ifdef QQQ_DRAIN_HELPERS
+        if (epi_tid == 0) {  // ticket (and "partials are published") for the unpack warps' share of this drain
+          __threadfence();
+          *reinterpret_cast<volatile uint32_t*>(misc + 2 + dbuf) = ((uint32_t)(seg + 1) << 16) | (uint32_t)ticket;
+        }
+#endif
       }
       const bool finish = whole || ticket == parts - 1;  // this CTA writes D for the tile
+#ifdef QQQ_DRAIN_HELPERS
+      mstep = (finish && (ndbuf == 1 || seg == n_seg - 1)) ? 64 : 16 * (n_epi >> 2);  // same rule as drain_share
+#endif
       const int others = (!whole && finish) ? parts - 1 : 0;  // published partial tiles the finisher adds
 
       // partial sums published by the other contributors, prefetched one 16-row chunk ahead (rows past `rows`
@@ -704,10 +749,6 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // Software-pipelined drain: the TMEM load of the next chunk is in flight while this one is converted and
       // stored (TMEM reads run at 64 B/clk per SM: 2048 cycles for a 128 x 256 accumulator).
       {
-#ifdef QQQ_DRAIN_HELPERS
-        // helped segments (same rule as drain_share): the quadrant's chunks go round 4 members, epilogue warps first
-        const int mstep = (whole && (ndbuf == 1 || seg == n_seg - 1)) ? 64 : 16 * (n_epi >> 2);
-#endif
         uint32_t ra[16], rb[16];
         int mb = 16 * eh;
         if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);

@@ -76,7 +76,9 @@ class CtaSim:
         """twin=True: CTA pair approximated by doubling this CTA's arrivals on the shared barriers.
         leader=<CtaSim>: this object is the PEER CTA (rank 1) of a faithfully modelled pair (see PairSim)."""
         self.p, self.rng, self.helpers = plan, (leader.rng if leader else random.Random(seed)), helpers
-        self.leader = leader
+        self.leader, self.seed = leader, seed
+        self.hinfo = {}  # dbuf -> segment whose ticket the epilogue has handed to the unpack warps
+        self.helper_done = {}  # unpack warp -> number of segments whose hand-off it has consumed
         self.segs = segments(plan, cta)
         self.KU, self.KSUB, self.G = plan["k_units"], plan["ksub"], plan["unpack_groups"]
         self.NSW, self.NST = plan["stages_w"], plan["stages_t"]
@@ -167,10 +169,17 @@ class CtaSim:
         mt = tile % self.m_tiles
         return min(self.n_tok, self.M - mt * self.n_tok)
 
-    def helped(self, sg):
+    def whole(self, sg):
         _, kb0, kb1 = self.segs[sg]
-        whole = kb0 == 0 and kb1 == self.KU
-        return self.helpers and whole and (self.ndbuf == 1 or sg == len(self.segs) - 1)
+        return kb0 == 0 and kb1 == self.KU
+
+    def finisher(self, sg):
+        """Whether this CTA finishes the tile of segment sg.  For split tiles that is decided by arrival order across
+        CTAs (ticket); the model draws it once per segment so that every role of the CTA sees the same answer."""
+        return self.whole(sg) or random.Random(hash((id(self.p) & 0xFFFF, self.seed, sg))).random() < 0.5
+
+    def helped(self, sg):
+        return self.helpers and self.finisher(sg) and (self.ndbuf == 1 or sg == len(self.segs) - 1)
 
     def drain(self, sg, q, first_chunk, step):
         rows = self.seg_rows(sg)
@@ -183,16 +192,21 @@ class CtaSim:
         st, as_ = Ring(self.NSW), Ring(self.NA)
         turn = 0
         h = {"seg": 0, "end": (self.segs[0][2] - self.segs[0][1]) if self.segs else 0}
+        self.helper_done[(grp, q)] = 0
 
         def drain_due(u):
             while h["seg"] < len(self.segs) and h["end"] - 1 + self.NA <= u:
                 sg = h["seg"]
                 dbuf, use = sg % self.ndbuf, sg // self.ndbuf
                 yield ("wait", self.dfull[dbuf], use & 1, use)
+                if not self.whole(sg):  # spin on misc[2 + dbuf] until the epilogue has published this segment's ticket
+                    while self.hinfo.get(dbuf) != sg:
+                        yield ("sleep", self.rng.randint(5, 50))
                 if self.helped(sg):
                     yield from self.drain(sg, q, self.n_epi // 4 + grp, 4)
                 self.dempty[dbuf].arrive(self.pair)
                 h["seg"] += 1
+                self.helper_done[(grp, q)] = h["seg"]
                 if h["seg"] < len(self.segs):
                     h["end"] += self.segs[h["seg"]][2] - self.segs[h["seg"]][1]
 
@@ -222,6 +236,20 @@ class CtaSim:
         for sg in range(len(self.segs)):
             dbuf, use = sg % self.ndbuf, sg // self.ndbuf
             yield ("wait", self.dfull[dbuf], use & 1, use)
+            if not self.whole(sg):
+                if e == 0:
+                    # ticket; the finisher also waits until the other contributors' partials are published (other CTAs,
+                    # never blocked by this one)
+                    yield ("sleep", self.rng.randint(20, 2000 if self.finisher(sg) else 100))
+                    if self.helpers:
+                        prev = self.hinfo.get(dbuf)
+                        assert prev is None or all(v > prev for v in self.helper_done.values()), (
+                            "ticket word overwritten before every unpack warp had read it")
+                        self.hinfo[dbuf] = sg
+                    self.ticket_ready = sg
+                else:  # named barrier of the epilogue warps around the ticket
+                    while getattr(self, "ticket_ready", -1) < sg:
+                        yield ("sleep", self.rng.randint(5, 50))
             step = 4 if self.helped(sg) else self.n_epi // 4
             yield from self.drain(sg, q, eh, step)
             self.dempty[dbuf].arrive(self.pair)
