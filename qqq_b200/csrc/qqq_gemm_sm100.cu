@@ -158,8 +158,9 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
 // frees at the moment the MMA completes segment s.  So before unpacking that unit, every unpack warp takes its share of
 // the drain of segment s: a quadrant's chunks go round its 4 members (n_epi/4 epilogue warps, then the G unpack warps).
 // Static membership: every unpack warp waits for and arrives on the accumulator barriers of EVERY segment (so that its
-// parity waits stay in step), but converts and stores only where it pays and is simple: whole tiles (no split-K ticket,
-// no partials), in single-buffer mode or for the CTA's last segment.
+// parity waits stay in step), but converts and stores only where it pays: tiles this CTA finishes (whole tiles, and split
+// tiles for which it drew the last ticket: the epilogue hands ticket and "partials are published" over through
+// misc[2 + dbuf]), in single-buffer mode or for the CTA's last segment.  Publishing a partial stays with the epilogue.
 //
 // One 16-token chunk of this lane's channel, whole-tile case: TMEM -> fp32 * s2 * s1 -> fp16 -> warp-private smem tile
 // -> 16-byte row stores (same arithmetic and order as the epilogue warps' `process`).
