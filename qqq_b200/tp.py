@@ -120,6 +120,8 @@ class _SymmMemBackend:
             pass
 
     def alloc(self, numel: int, device):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         t = self.symm.empty(numel, dtype=torch.float16, device=device)
         hdl = self.symm.rendezvous(t, self.group)
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
