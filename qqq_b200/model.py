@@ -138,7 +138,9 @@ def rtn_quantizers(model: nn.Module, group_size: int, bits: int = 4, names=None)
         W_fq, scale, zero, s_extra = rtn_quantize_weight(lin.weight.data, group_size, bits)
         lin.weight.data = W_fq.to(lin.weight.dtype)
         if s_extra is not None:
-            # like the reference, the 8-bit scale is taken from the weight as stored (after the cast above)
+            # like the reference (gptq.py:191-215) the 8-bit scale is taken from the weight as the layer stores it (after
+            # the cast to the layer's dtype); the Quantizer promotes to fp32 (`torch.minimum(x.min(1)[0], zeros_fp32)`,
+            # quant.py:70-72), so the maximum of the fp16 values and the division by 127 are fp32 operations
             amax = lin.weight.data.float().abs().max(1)[0]
             s_extra = (torch.where(amax == 0, torch.ones_like(amax), amax) / 127.0).reshape(-1, 1)
         g_idx = torch.arange(lin.in_features, device=scale.device) // (group_size if group_size != -1 else lin.in_features)

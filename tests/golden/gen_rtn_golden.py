@@ -65,6 +65,14 @@ def main():
         out = dict(W=W.numpy(), Q=Q.numpy(), scale=scale.numpy(), zero=zero.numpy())
         if s_extra is not None:
             out["s_extra"] = s_extra.numpy()
+            # the flow of GPTQ.fasterquant (gptq.py:191-215): the layer keeps Q in ITS dtype (fp16) and the 8-bit
+            # quantizer_extra runs on that fp16 tensor; find_params promotes to fp32 (quant.py:70-72)
+            Q16, _, _, _ = reference_rtn(mod, W.half().float(), gs)  # an fp16 layer: W itself is fp16
+            qe = mod.Quantizer()
+            qe.configure(bits=8, perchannel=True, groupsize=-1, sym=True, mse=False)
+            qe.find_params(Q16.half().clone(), weight=True)
+            out["s_extra_fp16_layer"] = qe.scale.float().numpy()
+            assert qe.scale.dtype == torch.float32
         name = f"rtn_N{N}_K{K}_g{'pc' if gs == -1 else gs}.npz"
         np.savez_compressed(os.path.join(HERE, name), **out)
         print("wrote", name, {k: v.shape for k, v in out.items()})

@@ -262,3 +262,22 @@ def test_share_scratch_keeps_results_and_releases_memory(oracle_backend):
         assert q.workspace.numel() >= q.outfeatures // 128 * q.max_par
     assert torch.equal(_logits(m, ids), ref)
     assert set(qmodel.quantized_state_dict(m)) == keys  # scratch stays out of checkpoints
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "rtn_*g128.npz"))), ids=os.path.basename)
+def test_rtn_quantizers_take_s_extra_from_the_stored_fp16_weight_like_the_reference(path):
+    """GPTQ.fasterquant stores Q in the layer's dtype and runs the 8-bit quantizer_extra on that tensor (gptq.py:191-215):
+    the scale comes from the fp16-rounded weights, evaluated in fp32 (the Quantizer promotes, quant.py:70-72)."""
+    g = np.load(path)
+
+    class Holder(nn.Module):
+        def __init__(self, W):
+            super().__init__()
+            self.layers = nn.ModuleList([nn.Linear(W.shape[1], W.shape[0], bias=False)])
+            self.layers[0].weight.data = torch.from_numpy(W).half()
+
+    m = Holder(g["W"])  # an fp16 layer holding W
+    q = qmodel.rtn_quantizers(m, 128, names=["layers.0"])["layers.0"]
+    s_extra = q[3]
+    assert s_extra.dtype == torch.float32
+    assert np.array_equal(s_extra.numpy(), g["s_extra_fp16_layer"])
