@@ -89,3 +89,85 @@ def test_shim_is_positional_only_like_pybind(reference_module):
         shim.qqq_gemm(A=None)
     with pytest.raises(TypeError):
         shim.qqq_gemm(*([None] * 8))  # the C++ defaults are invisible to Python: all twelve are required
+
+
+CTOR_CASES = [
+    dict(bits=4, group_size=-1, infeatures=256, outfeatures=256, bias=False),
+    dict(bits=4, group_size=128, infeatures=512, outfeatures=128, bias=True),
+    dict(bits=4, group_size=256, infeatures=256, outfeatures=64, bias=False),   # group_size == infeatures: per-channel format
+    dict(bits=4, group_size=-1, infeatures=192, outfeatures=256, bias=False),   # (64, 256) tile rule
+    dict(bits=4, group_size=-1, infeatures=100, outfeatures=256, bias=False),   # unsupported shape
+    dict(bits=4, group_size=-1, infeatures=256, outfeatures=96, bias=False),    # unsupported shape
+    dict(bits=8, group_size=-1, infeatures=256, outfeatures=256, bias=False),   # only 4 bits
+    dict(bits=4, group_size=64, infeatures=256, outfeatures=256, bias=False),   # only -1 / 128 / infeatures
+    dict(bits=4, group_size=-1, infeatures=256, outfeatures=256, bias=False, trainable=True),
+]
+
+
+@pytest.mark.parametrize("kw", CTOR_CASES, ids=[str(i) for i in range(len(CTOR_CASES))])
+def test_constructor_parity_with_the_reference_module(reference_module, kw):
+    """Same acceptance rule, same exception types and texts, same buffers (names, shapes, dtypes, persistence), same maxq
+    (QQQ/gptq/qlinear/qlinear_marlin.py:51-139)."""
+    import qqq_b200
+
+    mod, _ = reference_module
+
+    def build(cls):
+        try:
+            return cls(**kw), None
+        except Exception as e:  # noqa: BLE001
+            return None, e
+
+    ref, ref_err = build(mod.QuantLinear)
+    ours, our_err = build(qqq_b200.QuantLinear)
+    if ref_err is not None:
+        assert our_err is not None, f"reference raises {ref_err!r}, ours accepts"
+        assert type(our_err) is type(ref_err) and str(our_err) == str(ref_err)
+        return
+    assert our_err is None, f"ours raises {our_err!r}, reference accepts"
+    rb, ob = dict(ref.named_buffers()), dict(ours.named_buffers())
+    assert set(rb) == set(ob)
+    for k in rb:
+        assert rb[k].shape == ob[k].shape and rb[k].dtype == ob[k].dtype, k
+    assert set(ref.state_dict()) == set(ours.state_dict())
+    for attr in ("infeatures", "outfeatures", "group_size", "bits", "maxq", "max_par", "tile"):
+        assert getattr(ref, attr) == getattr(ours, attr), attr
+    # scale dtypes stay pinned through .half() / .to(dtype) on both (qlinear_marlin.py:141-145)
+    assert ours.half().s_channel.dtype == ref.half().s_channel.dtype == torch.float32
+
+
+def test_pack_requires_s_extra_for_per_group_on_both(reference_module):
+    import qqq_b200
+
+    mod, _ = reference_module
+    lin = torch.nn.Linear(256, 128, bias=False).half()
+    scales = torch.full((128, 2), 0.01)
+    for cls in (mod.QuantLinear, qqq_b200.QuantLinear):
+        ql = cls(4, 128, 256, 128, bias=False)
+        with pytest.raises(AssertionError, match="s_extra is needed"):
+            ql.pack(lin, scales)
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_pack_of_extreme_and_clamped_values_matches_the_reference(reference_module, gs):
+    """Weights beyond the grid (clamped by pack), exact half-way cases (round-half-even) and negative zero."""
+    import qqq_b200
+
+    mod, _ = reference_module
+    K, N = 256, 128
+    g = torch.Generator().manual_seed(77)
+    scales = (torch.rand(N, 1 if gs == -1 else K // 128, generator=g) * 0.02 + 0.005)
+    grid = torch.randint(-12, 20, (N, K), generator=g).float() + torch.tensor([0.0, 0.5, -0.5, 0.0])[torch.randint(0, 4, (N, K), generator=g)]
+    s_rep = scales if gs == -1 else scales.repeat_interleave(128, dim=1)
+    lin = torch.nn.Linear(K, N, bias=False).half()
+    lin.weight.data = (grid * s_rep).half()
+    lin.weight.data[0, :4] = torch.tensor([-0.0, 0.0, 65504.0, -65504.0], dtype=torch.half)
+    s_extra = None if gs == -1 else (lin.weight.data.float().abs().amax(1).clamp_min(1e-6) / 127.0).reshape(1, N)
+    ref = mod.QuantLinear(4, gs, K, N, bias=False)
+    ours = qqq_b200.QuantLinear(4, gs, K, N, bias=False)
+    ref.pack(lin, scales, s_extra)
+    ours.pack(lin, scales, s_extra)
+    for name in ("B", "s_channel", "s_group"):
+        a, b = getattr(ref, name), getattr(ours, name)
+        assert a.shape == b.shape and torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a.view(torch.int16) if a.dtype == torch.half else a,
+                                                    b.view(torch.int32) if b.dtype == torch.float32 else b.view(torch.int16) if b.dtype == torch.half else b), name
