@@ -66,6 +66,17 @@ int qqq_gemm_reduce_sm100a(const void* A, const void* B, void* C, void* D_multic
                            int dev, void* stream /* cudaStream_t */, int thread_k, int thread_n, int sms, int max_par);
 
 /*
+ * The same GEMM without its epilogue scales: D_int32[M,N] (int32, row-major) = A[M,K] (int8) x W8[K,N], the exact integer
+ * accumulators.  For the bit-exact tensor-parallel mode of row shards: every rank quantises its K-shard
+ * of the activations with the SHARED per-token scale (all-reduce-max of the row maxima), the int32 partial sums are
+ * all-reduced (exact), and f16((f32(acc) * s2[n]) * s1[m]) is applied once — the result equals the 1-GPU output bit for
+ * bit (qqq_b200/tp.py: ExactRowParallelQuantLinear).  s1 / s2 are not arguments; scratch contract as qqq_gemm_sm100a.
+ */
+int qqq_gemm_acc_sm100a(const void* A, const void* B, void* C, void* D_int32, const void* s3, int prob_m, int prob_n,
+                        int prob_k, void* workspace, int groupsize, int dev, void* stream /* cudaStream_t */, int sms,
+                        int max_par);
+
+/*
  * Per-token dynamic int8 quantisation of activations, bit-identical to
  * QQQ/gptq/qlinear/qlinear_marlin.py:265-268:
  *   s1[m] = fp32( fp16( max_k |x[m,k]| / 127 ) );   q[m,k] = int8( clamp( rint( x[m,k] / s1[m] ), -128, 127 ) )

@@ -16,6 +16,7 @@ LIB_PATH = _HERE / "libqqq_b200.so"
 SYMBOLS = (
     "qqq_gemm_sm100a",
     "qqq_gemm_reduce_sm100a",
+    "qqq_gemm_acc_sm100a",
     "qqq_act_quant_sm100a",
     "qqq_act_quant_strided_sm100a",
     "qqq_b200_version",
@@ -50,6 +51,8 @@ def load() -> ctypes.CDLL:
     lib.qqq_gemm_sm100a.restype = ci
     lib.qqq_gemm_reduce_sm100a.argtypes = list(lib.qqq_gemm_sm100a.argtypes)
     lib.qqq_gemm_reduce_sm100a.restype = ci
+    lib.qqq_gemm_acc_sm100a.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, ci]
+    lib.qqq_gemm_acc_sm100a.restype = ci
     lib.qqq_act_quant_sm100a.argtypes = [vp, vp, vp, ci, ci, ci, vp]
     lib.qqq_act_quant_sm100a.restype = ci
     lib.qqq_act_quant_strided_sm100a.argtypes = [vp, ctypes.c_longlong, vp, vp, ci, ci, ci, vp]

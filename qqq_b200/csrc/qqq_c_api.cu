@@ -367,7 +367,7 @@ int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_coun
 
 static int gemm_impl(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
                      int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
-                     int thread_k, int thread_n, int sms, int max_par, bool reduce) {
+                     int thread_k, int thread_n, int sms, int max_par, bool reduce, bool acc = false) {
   using namespace qqq;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int M = prob_m, N = prob_n, K = prob_k;
@@ -432,10 +432,11 @@ static int gemm_impl(const void* A, const void* B, void* C, void* D, const void*
   int grid = 0;
   {
     const int rc = plan_gemm(M, N, K, grouped, sm_count, max_par, C != nullptr && workspace != nullptr, p, &grid,
-                             /*allow_pair=*/!reduce);
+                             /*allow_pair=*/!reduce && !acc);
     if (rc != QQQ_OK) return rc;
   }
   p.reduce = reduce ? 1 : 0;
+  p.acc = acc ? 1 : 0;
   // weights are streamed once when a single token tile covers M; tokens are re-read by every CTA
   p.hint_b = p.m_tiles == 1 ? kEvictFirst : kEvictNormal;
   p.hint_a = kEvictLast;
@@ -471,6 +472,12 @@ int qqq_gemm_reduce_sm100a(const void* A, const void* B, void* C, void* D_multic
                            void* stream_, int thread_k, int thread_n, int sms, int max_par) {
   return gemm_impl(A, B, C, D_multicast, s1, s2, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, thread_k,
                    thread_n, sms, max_par, true);
+}
+
+int qqq_gemm_acc_sm100a(const void* A, const void* B, void* C, void* D_int32, const void* s3, int prob_m, int prob_n,
+                        int prob_k, void* workspace, int groupsize, int dev, void* stream_, int sms, int max_par) {
+  return gemm_impl(A, B, C, D_int32, nullptr, nullptr, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, -1, -1,
+                   sms, max_par, false, true);
 }
 
 int qqq_act_quant_strided_sm100a(const void* x, long long ldx, void* q, void* s1, int prob_m, int prob_k, int dev,

@@ -195,7 +195,9 @@ __device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t
 }
 #endif
 
-template <bool GROUPED, bool kPair, bool kReduce = false>
+// kAcc (qqq_gemm_acc_sm100a): the finished tile leaves as the raw int32 accumulators, row-major [M, N] int32, no scales —
+// for the bit-exact tensor-parallel mode (int32 partial sums are all-reduced, the scales applied once afterwards).
+template <bool GROUPED, bool kPair, bool kReduce = false, bool kAcc = false>
 __global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
@@ -470,7 +472,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         __threadfence();  // reads of the published partials come after the epilogue's acquire
       }
       const bool finish = whole || ticket == parts - 1;
-      const bool help = where && finish;  // publishers' partial stores stay with the epilogue warps (they announce them)
+      // publishers' partial stores stay with the epilogue warps (they announce them); raw-accumulator launches (kAcc) too
+      const bool help = where && finish && !kAcc;
       if (help) {
         if (!h_dep_waited) {  // s1 comes from the preceding kernel; D may still be in use by it
           grid_dependency_wait();
@@ -643,7 +646,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const bool whole = (kb0 == 0 && kb1 == KU);
       // contributors of a phase-A tile: the CTAs whose slice [b*a_upc, (b+1)*a_upc) meets the tile's units
       const int parts = whole ? 1 : (tile * KU + KU - 1) / p.a_upc - (tile * KU) / p.a_upc + 1;
-      const float s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;
+      float s2v = 0.f;
+      if constexpr (!kAcc) s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;  // kAcc: no scales (s1 / s2 are null)
       // Partial tiles of split-K live in C as compact [n_tok][128] int32 blocks, block index =
       // (ticket * a_tiles + tile): a chunk's 16 rows are 512 B apart, so the 16 stores / loads of a lane use one base
       // register and immediate offsets (no serial address chain), and each of them is one full 128-byte line per warp.
@@ -653,7 +657,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // per-token scales of this token tile -> smem (once per tile change), so the store loop has no global loads
       if (mt != staged_mt) {
         named_bar_sync(1, n_epi_thr);  // previous users of s1_sm are done
-        for (int i = epi_tid; i < p.n_tok; i += n_epi_thr) s1_sm[i] = (m0 + i < p.M) ? __ldg(p.s1 + m0 + i) : 0.f;
+        if constexpr (!kAcc)
+          for (int i = epi_tid; i < p.n_tok; i += n_epi_thr) s1_sm[i] = (m0 + i < p.M) ? __ldg(p.s1 + m0 + i) : 0.f;
         named_bar_sync(1, n_epi_thr);
         staged_mt = mt;
       }
@@ -691,7 +696,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       const bool finish = whole || ticket == parts - 1;  // this CTA writes D for the tile
 #ifdef QQQ_DRAIN_HELPERS
-      mstep = (finish && (ndbuf == 1 || seg == n_seg - 1)) ? 64 : 16 * (n_epi >> 2);  // same rule as drain_share
+      mstep = (finish && !kAcc && (ndbuf == 1 || seg == n_seg - 1)) ? 64 : 16 * (n_epi >> 2);  // same rule as drain_share
 #endif
       const int others = (!whole && finish) ? parts - 1 : 0;  // published partial tiles the finisher adds
 
@@ -717,7 +722,15 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           for (int i = 0; i < 16; ++i) r[i] += (uint32_t)pre[i];
           if (mb + mstep < rows) fetch_partials(mb + mstep, pre);
         }
-        if (finish) {
+        if (finish && kAcc) {
+          // lane = channel, i = token: every store instruction of the warp writes 32 consecutive int32 of one row
+          if (n_ok) {
+            int* __restrict__ d32 = reinterpret_cast<int*>(p.D) + (size_t)(m0 + mb) * p.N + n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (mb + i < rows) d32[(size_t)i * p.N] = (int)r[i];
+          }
+        } else if (finish) {
           unsigned short* sp = stg + lane;
           const float4* s4 = reinterpret_cast<const float4*>(s1_sm + mb);
 #pragma unroll
@@ -817,16 +830,19 @@ size_t gemm_smem_bytes(const GemmParams& p) {
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
-  static bool attr_set[6][64] = {};  // the opt-in shared-memory attribute is per device
+  static bool attr_set[8][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
-  if (p.reduce && p.pair) return cudaErrorInvalidValue;  // the planner never pairs a reducing launch
-  const int variant = p.reduce ? 4 + (grouped ? 1 : 0) : (grouped ? 1 : 0) + (p.pair ? 2 : 0);
+  if ((p.reduce || p.acc) && p.pair) return cudaErrorInvalidValue;  // the planner never pairs these launches
+  if (p.reduce && p.acc) return cudaErrorInvalidValue;
+  const int variant = p.acc ? 6 + (grouped ? 1 : 0) : p.reduce ? 4 + (grouped ? 1 : 0) : (grouped ? 1 : 0) + (p.pair ? 2 : 0);
   auto kern = variant == 0 ? qqq_gemm_kernel<false, false>
             : variant == 1 ? qqq_gemm_kernel<true, false>
             : variant == 2 ? qqq_gemm_kernel<false, true>
             : variant == 3 ? qqq_gemm_kernel<true, true>
             : variant == 4 ? qqq_gemm_kernel<false, false, true>
-                           : qqq_gemm_kernel<true, false, true>;
+            : variant == 5 ? qqq_gemm_kernel<true, false, true>
+            : variant == 6 ? qqq_gemm_kernel<false, false, false, true>
+                           : qqq_gemm_kernel<true, false, false, true>;
   if (dev < 0 || dev >= 64 || !attr_set[variant][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) return e;

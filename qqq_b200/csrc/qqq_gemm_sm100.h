@@ -63,6 +63,7 @@ struct GemmParams {
   int b_tpc;
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
   int reduce;               // 1: D is a multicast address and the epilogue adds into it (multimem.red) instead of storing
+  int acc;                  // 1: D is int32 [M, N] and receives the raw accumulators (no scales)
 };
 
 size_t gemm_smem_bytes(const GemmParams& p);

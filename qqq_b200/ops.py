@@ -145,3 +145,23 @@ def dynamic_quant(x: torch.Tensor):
 
 def launch_count() -> int:
     return int(_lib.load().qqq_b200_launch_count())
+
+
+def qqq_gemm_acc(A, B, C, D32, s3, workspace, max_par=16, sms=-1):
+    """The W4A8 GEMM without its epilogue scales: D32 int32 [M, N] receives the exact integer accumulators
+    (qqq_gemm_acc_sm100a in include/qqq_b200.h) — building block of the bit-exact tensor-parallel mode."""
+    prob_m, prob_k, prob_n = A.size(0), A.size(1), C.size(1)
+    groupsize = -1 if s3.numel() == 0 else prob_k // s3.size(0)
+    if not A.is_cuda:
+        raise RuntimeError("qqq_gemm_acc: tensors must be CUDA tensors (qqq_b200 has no CPU path).")
+    if D32.dtype != torch.int32 or tuple(D32.shape) != (prob_m, prob_n) or not D32.is_contiguous():
+        raise RuntimeError("qqq_gemm_acc: D32 must be a contiguous int32 [M, N] tensor.")
+    if workspace.numel() < prob_n // 128 * max_par or C.size(0) < 64 * max_par:
+        raise RuntimeError("qqq_gemm_acc: workspace / C too small.")
+    dev = A.get_device()
+    err = _lib.load().qqq_gemm_acc_sm100a(
+        _ptr(A), _ptr(B), _ptr(C), _ptr(D32), _ptr(s3) if s3.numel() else None, prob_m, prob_n, prob_k, _ptr(workspace),
+        groupsize, dev, torch.cuda.current_stream(dev).cuda_stream, sms, max_par,
+    )
+    if err != 0:
+        raise RuntimeError(f"qqq_gemm_acc_sm100a failed (rc={err}): {_lib.last_error()}")

@@ -102,6 +102,61 @@ class RowParallelQuantLinear(nn.Module):
         return y
 
 
+def _replicated_bias(shard: QuantLinear, group=None):
+    """`shard_quant_linear(..., "row")` keeps the bias on rank 0 only (it is added once, before the all-reduce).  Modules
+    that add it AFTER their reduction need it on every rank: broadcast it from rank 0 of the group (collective call)."""
+    dev = shard.B.device
+    flag = torch.tensor([1 if shard.bias is not None else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()) == 0:
+        return None
+    b = shard.bias.clone() if shard.bias is not None else torch.empty(shard.outfeatures, dtype=torch.half, device=dev)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(b, src=src, group=group)
+    return b
+
+
+class ExactRowParallelQuantLinear(nn.Module):
+    """Row-parallel linear whose output equals the 1-GPU QuantLinear's BIT FOR BIT ("exact" mode):
+
+      1. the per-token scale is shared: all-reduce-MAX of the ranks' row maxima of |x_local| (a [M] vector), then the
+         reference's own scale expression on it — the same s1 the 1-GPU module computes from the full row;
+      2. every rank quantises its K-shard with that s1 (the reference's eager expression, qlinear_marlin.py:267) and runs
+         the GEMM without epilogue scales (qqq_gemm_acc_sm100a): exact int32 partial sums;
+      3. all-reduce-SUM of the int32 [M, N] partials (exact in any order; 2x the bytes of the fp16 mode);
+      4. f16((f32(acc) * s2[n]) * s1[m]) once, in the reference's order (csrc/qqq_gemm.cu:695-700).
+
+    Costs two collectives and twice the bytes; RowParallelQuantLinear / FusedRowParallelQuantLinear are the fast modes."""
+
+    def __init__(self, shard: QuantLinear, group=None):
+        super().__init__()
+        self.shard = shard
+        self.group = group
+        from .qlinear import _scale_perm_positions
+
+        _, sp32 = _scale_perm_positions(shard.s_channel.device)
+        inv = torch.empty_like(sp32)
+        inv[sp32] = torch.arange(32, device=sp32.device)
+        self.register_buffer("_unperm32", inv, persistent=False)  # natural channel n sits at permuted position inv[n % 32]
+        self.bias = _replicated_bias(shard, group)
+
+    def forward(self, x_local):
+        ql = self.shard
+        out_shape = x_local.shape[:-1] + (ql.outfeatures,)
+        A = x_local.reshape(-1, x_local.shape[-1]).half()
+        amax = A.abs().max(dim=-1, keepdim=True)[0]
+        dist.all_reduce(amax, op=dist.ReduceOp.MAX, group=self.group)
+        s1 = amax.div(127.0).to(torch.float32)  # the reference's expression on the full-row maximum
+        A8 = (A / s1).round().clamp(-128, 127).to(torch.int8)
+        acc = torch.empty(A.shape[0], ql.outfeatures, dtype=torch.int32, device=A.device)
+        ops.qqq_gemm_acc(A8, ql.B, ql.reduce_buffer, acc, ql.s_group, ql.workspace, ql.max_par)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
+        N = ql.outfeatures
+        s2 = ql.s_channel.reshape(N // 32, 32)[:, self._unperm32].reshape(1, N)  # natural channel order
+        out = ((acc.to(torch.float32) * s2) * s1).to(torch.float16).reshape(out_shape)
+        return out + self.bias if self.bias is not None else out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # GEMM + all-reduce in one kernel (SURVEY.md §8f row N4)
 # ---------------------------------------------------------------------------------------------------------------
@@ -185,6 +240,7 @@ class FusedRowParallelQuantLinear(nn.Module):
         super().__init__()
         self.shard = shard
         object.__setattr__(self, "ws", workspace)
+        self.bias = _replicated_bias(shard, getattr(workspace.backend, "group", None))
 
     def forward(self, x_local):
         ql = self.shard
@@ -196,4 +252,4 @@ class FusedRowParallelQuantLinear(nn.Module):
                             ql.max_par)
         self.ws.end()
         out = out.reshape(out_shape)
-        return out + ql.bias if ql.bias is not None else out
+        return out + self.bias if self.bias is not None else out

@@ -60,6 +60,8 @@ def test_empty_problem_returns_ok_without_device():
     lib = _lib.load()
     assert lib.qqq_gemm_sm100a(None, None, None, None, None, None, None, 0, 128, 128, None, -1, 0, None, -1, -1, -1, 16) == 0
     assert lib.qqq_gemm_reduce_sm100a(None, None, None, None, None, None, None, 0, 128, 128, None, -1, 0, None, -1, -1, -1, 16) == 0
+    assert lib.qqq_gemm_acc_sm100a(None, None, None, None, None, 0, 128, 128, None, -1, 0, None, -1, 16) == 0
+    assert lib.qqq_gemm_acc_sm100a(None, None, None, None, None, 4, 100, 128, None, -1, 0, None, -1, 16) == 1
     assert lib.qqq_act_quant_sm100a(None, None, None, 0, 128, 0, None) == 0
     assert lib.qqq_act_quant_sm100a(None, None, None, 4, 100, 0, None) == 1
 

@@ -209,3 +209,55 @@ def test_fused_row_parallel_protocol_gloo(gs):
     assert ok, "workspace protocol: shapes, buffer lifetime or barrier count wrong"
     # per-shard activation scales: tolerance parity against the full-K result (relative to the batch's own max, M down to 1)
     assert worst <= 6e-2, f"fused row-parallel relative error {worst}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# exact mode: shared s1 + int32 partial sums -> bit-equal to the 1-GPU module
+# ---------------------------------------------------------------------------------------------------------------
+def _exact_worker(rank, world, port, gs, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import qqq_oracle as O
+    from qqq_b200 import ops, tp
+
+    def gemm_acc(A, B, C, D32, s3, workspace, max_par=16, sms=-1):  # the C-ABI call on the oracle's integer model
+        W8 = O.weights_int8(B.numpy(), s3.numpy() if s3.numel() else None)
+        D32.copy_(torch.from_numpy((A.numpy().astype(np.int64) @ W8.astype(np.int64)).astype(np.int32)))
+
+    ops.qqq_gemm_acc = gemm_acc
+    M, K, N = 9, 512, 256
+    p = O.make_problem(M, K, N, gs, seed=41)
+    full = _full_module(p, K, N, gs)
+    full.bias = torch.linspace(-2, 2, N).half()
+    # what the 1-GPU module computes (torch CPU evaluates .div(127.0) as a true division: cuda_semantics=False)
+    A8, s1 = O.dynamic_quant(p["x"], cuda_semantics=False)
+    want = torch.from_numpy(O.qqq_gemm_oracle(A8, p["B"], s1, p["s2"], p["s3"])) + full.bias
+    shard = tp.shard_quant_linear(full, rank, world, "row")
+    assert (shard.bias is not None) == (rank == 0)
+    mod = tp.ExactRowParallelQuantLinear(shard)
+    _, offs = tp.split_sizes(K, world, 128 if gs != -1 else 64)
+    y = mod(torch.from_numpy(p["x"][:, offs[rank]:offs[rank + 1]].copy()).reshape(3, 3, -1))
+    ok = y.shape == (3, 3, N) and torch.equal(y.reshape(M, N).view(torch.int16), want.view(torch.int16))
+    flags = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(bool(flags.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_exact_row_parallel_is_bit_equal_to_one_gpu_gloo(gs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exact_worker, args=(r, 2, port, gs, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    ok = q.get(timeout=240)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert ok, "exact row-parallel mode must reproduce the 1-GPU output bit for bit on every rank (bias included)"

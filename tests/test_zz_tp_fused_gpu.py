@@ -62,7 +62,11 @@ def _worker(rank, world, port, gs, out):
         err_sum = float((y_fused.float() - part).abs().max())
         err_nccl = float((y_fused.float() - y_nccl.float()).abs().max())
         scale = float(part.abs().max())
-        res.append((M, err_sum, err_nccl, scale, n_launch, tuple(y_fused.shape), int(shard.workspace.abs().sum())))
+        # exact mode: shared s1 + int32 partial sums -> the 1-GPU module's output bit for bit
+        y_exact = tp.ExactRowParallelQuantLinear(shard)(x_loc)
+        y_one = full.to(dev)(torch.from_numpy(p["x"]).to(dev))
+        exact_ok = bool(torch.equal(y_exact.view(torch.int16), y_one.view(torch.int16)))
+        res.append((M, err_sum, err_nccl, scale, n_launch, tuple(y_fused.shape), int(shard.workspace.abs().sum()), exact_ok))
     if rank == 0:
         out.put(res)
     dist.barrier()
@@ -90,8 +94,9 @@ def test_fused_gemm_allreduce_matches_nccl_path(gs):
         for pr in procs:
             if pr.is_alive():
                 pr.kill()
-    for (M, err_sum, err_nccl, scale, n_launch, shape, ws_sum) in res:
+    for (M, err_sum, err_nccl, scale, n_launch, shape, ws_sum, exact_ok) in res:
         assert shape == (M, 512) and n_launch == 2 and ws_sum == 0
+        assert exact_ok, f"exact row-parallel mode differs from the 1-GPU module at M={M}"
         # one fp16 rounding of a value of magnitude <= scale: half an ulp = scale * 2^-11
         assert err_sum <= scale * 2.0 ** -10 + 1e-6, (M, err_sum, scale)
         assert err_nccl <= scale * 2.0 ** -9 + 1e-6, (M, err_nccl, scale)
