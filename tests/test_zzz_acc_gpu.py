@@ -1,5 +1,7 @@
 """GPU: qqq_gemm_acc (the GEMM without epilogue scales, raw int32 accumulators — building block of the bit-exact
-tensor-parallel mode) against the oracle's integer model, incl. shapes whose tiles are split along K (fix-up path)."""
+tensor-parallel mode) against the oracle's integer model, incl. shapes whose tiles are split along K (fix-up path).
+Named test_zzz_*: this kernel variant has not run on hardware yet (written after round 1's GPU budget was spent), so it
+goes last — a fault in it must not take the CUDA context away from the other GPU tests."""
 import numpy as np
 import pytest
 import torch
