@@ -18,7 +18,7 @@
 //                              fragment, so the weight tile becomes the UMMA A operand in TMEM without any
 //                              shuffle, shared-memory round trip or load-time repack.
 //   warp 1  MMA issuer       : tcgen05.mma.cta_group::1.kind::i8, A from TMEM, B (tokens) from a smem descriptor,
-//                              int32 accumulators in TMEM (double-buffered when n_tok <= 128)
+//                              int32 accumulators in TMEM (double-buffered when n_tok <= kDbufMaxTok = 192)
 //   4-8 epilogue warps       : tcgen05.ld -> fp32 * s2[n] * s1[m] (reference order, :695-700) -> fp16 -> D
 //
 // The two smem rings are decoupled: weight stages are released by the unpack warps as soon as they are in
@@ -29,6 +29,11 @@
 // several CTAs is reduced through `C`: every contributor stores its int32 partial tile into its own slot (plain
 // coalesced stores), the last CTA to arrive (lock counter in `workspace`) sums the slots in a fixed order (exact,
 // deterministic), applies the scales, writes D and resets the lock.
+//
+// Template variants of the one kernel: kPair (cluster of 2, cta_group::2: each CTA loads half of the token tile, the
+// leader issues UMMA M = 256 for both), kReduce (tensor-parallel row shards: the epilogue adds into a multicast D with
+// multimem.red instead of storing), kAcc (raw int32 accumulators out, for the bit-exact tensor-parallel mode); the
+// experiment builds -DQQQ_DBUF_MAX_TOK=208 and -DQQQ_DRAIN_HELPERS are described where they apply.
 #include "qqq_common.cuh"
 #include "qqq_gemm_sm100.h"
 
