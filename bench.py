@@ -481,7 +481,7 @@ def main():
                     help="N > 1: row-parallel linears reduce in their own epilogue (tp.FusedRowParallelQuantLinear)")
     ap.add_argument("--no-decode", action="store_true", help="skip the Llama-3-8B g128 decode section (configs[2])")
     ap.add_argument("--no-full", action="store_true", help="skip the whole-model (HF Llama forward) section")
-    ap.add_argument("--aux-budget", type=float, default=600.0, help="seconds the auxiliary sections may take in total")
+    ap.add_argument("--aux-budget", type=float, default=300.0, help="seconds the auxiliary sections may take in total")
     args = ap.parse_args()
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
