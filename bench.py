@@ -6,18 +6,25 @@
         bench.py --gpus N --steps K --warmup W
 
 Workload of a "step" (config.workload): every quantized Linear of Llama-2-7B (32 layers x {q,k,v,o,gate,up,down},
-per-channel W4A8), prefill seq=1024 batch=1  ->  BASELINE.json configs[1].  A step = for each of the 224 linears:
-fused per-token activation quant + tcgen05 W4A8 GEMM (through QuantLinear.forward -> C ABI).  Everything between the
+per-channel W4A8), prefill seq=1024 batch=1  ->  BASELINE.json configs[1].  The 224 linears are called module by module in
+the reference model's order through QuantLinear.forward -> C ABI (fused per-token activation quant + tcgen05 W4A8 GEMM);
+linears that consume the same tensor (q/k/v, gate/up) share its int8 quantisation (`set_act_quant_cache`, bit-identical:
+4 activation quants + 7 GEMMs per layer; the 7 + 7 structure is reported as `per_module_quant`).  Everything between the
 linears (attention, norms, SwiGLU) is outside the reference's hot path and is not executed; shapes chain as
 h -> q,k,v ; o(q) -> h' ; gate,up(h') ; down(gate) -> h.  tokens/s = 1024 / step time.
-The same JSON line carries the GEMM sweep of configs[4] (TFLOP/s and speed-up over fp16 cuBLAS at
-M in {1,16,128,1024,4096}, K=8192, N=21760, per-channel and g=128) under "gemm_sweep".
+The same JSON line carries the GEMM sweep of configs[4] (TFLOP/s, speed-up over fp16 cuBLAS and over the reference's own
+CUDA kernel at M in {1,16,128,1024,4096}, K=8192, N=21760, per-channel and g=128) under "gemm_sweep", configs[2] under
+"decode_g128", and at N > 1 the tensor-parallel sweep ("gemm_sweep_tp"), configs[3] ("llama2_70b_tp") and "tp_parity".
 
-N > 1: tensor parallel (strong scaling, same model): q,k,v,gate,up split N (no collective), o/down split K + one
-NCCL all-reduce of the fp16 [1024,4096] output per layer.
+N > 1: tensor parallel (strong scaling, same model): q,k,v,gate,up split N (no collective); o/down split K and exchange
+through the kernels themselves (--tp-mode scatter, default): the GEMM epilogue stores every output row into the
+partial-sum slot of the rank that owns it (peer stores over NVLink), the owner sums, quantises per token and multicasts
+the int8 rows to all ranks — reduce-scatter + all-gather fused into the GEMM and the activation quant, no NCCL call in
+the step.  --tp-mode nccl: one NCCL all-reduce of the fp16 [1024,4096] output per row-parallel layer;
+--tp-mode reduce: one-shot all-reduce in the GEMM epilogue (multimem.red).
 
 --impl reference: the dequant-to-fp16 torch.matmul CPU path (the oracle port; the reference has no CPU implementation
-of its own) on this box's host cores, on a bounded sample of the same workload.
+of its own) on this box's host cores: all 32 layers of the same workload per step.
 """
 from __future__ import annotations
 
@@ -36,32 +43,32 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-MODEL = dict(name="llama-2-7b", layers=32, hidden=4096, inter=11008, seq=1024, batch=1)
-# (name, K, N, parallel mode)
-LAYER_LINEARS = [("q", "hidden", "hidden", "column"), ("k", "hidden", "hidden", "column"),
-                 ("v", "hidden", "hidden", "column"), ("o", "hidden", "hidden", "row"),
-                 ("gate", "hidden", "inter", "column"), ("up", "hidden", "inter", "column"),
-                 ("down", "inter", "hidden", "row")]
+MODEL = dict(name="llama-2-7b", layers=32, hidden=4096, inter=11008, kv=4096, seq=1024, batch=1)
+LLAMA2_70B = dict(name="llama-2-70b", layers=80, hidden=8192, inter=28672, kv=1024, seq=1024, batch=1)
+UMMA_I8_PEAK_TOPS = 4428.0  # tcgen05.mma kind::i8 alone on this pool's B200 (profiles/r01/probe_umma_i8.log)
+
+
+def layer_linears(spec):
+    """(name, K, N, parallel mode) of the seven quantized linears of a decoder layer (QQQ/gptq/models/llama.py:202-229,275-283)."""
+    h, i, kv = spec["hidden"], spec["inter"], spec["kv"]
+    return [("q", h, h, "column"), ("k", h, kv, "column"), ("v", h, kv, "column"), ("o", h, h, "row"),
+            ("gate", h, i, "column"), ("up", h, i, "column"), ("down", i, h, "row")]
+
+
+GEMM_NAMES = ("q", "k", "v", "o", "gate", "up", "down")
 
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def model_flops(M):
-    f = 0
-    for (_, k, n, _) in LAYER_LINEARS:
-        f += 2.0 * M * MODEL[k] * MODEL[n]
-    return f * MODEL["layers"]
+def model_flops(spec, M):
+    return sum(2.0 * M * K * N for (_, K, N, _) in layer_linears(spec)) * spec["layers"]
 
 
-def model_gemm_bytes(M):
-    """Algorithmic bytes of the 224 GEMMs: M*K + K*N/2 + 2*M*N + 4*M + 4*N each."""
-    b = 0
-    for (_, k, n, _) in LAYER_LINEARS:
-        K, N = MODEL[k], MODEL[n]
-        b += M * K + K * N / 2 + 2 * M * N + 4 * M + 4 * N
-    return b * MODEL["layers"]
+def model_gemm_bytes(spec, M):
+    """Algorithmic bytes of the GEMMs: M*K + K*N/2 + 2*M*N + 4*M + 4*N each."""
+    return sum(M * K + K * N / 2 + 2 * M * N + 4 * M + 4 * N for (_, K, N, _) in layer_linears(spec)) * spec["layers"]
 
 
 def load_peaks():
@@ -132,35 +139,62 @@ def random_packed(K, N, gen, dev):
     return torch.randint(-2**31, 2**31 - 1, (K // 16, 2 * N), dtype=torch.int32, device=dev, generator=gen)
 
 
-def build_model(dev, rank, world, gen):
-    """Random-init Llama-2-7B quantized linears (per-channel), already sharded for `world` ranks."""
+def shard_dims(K, N, mode, rank, world):
+    """This rank's (K, N) of a linear: column = split N, row = split K, both in blocks of 64 (tp.split_sizes)."""
+    from qqq_b200 import tp
+
+    if world > 1:
+        if mode == "column":
+            N = tp.split_sizes(N, world, 64)[0][rank]
+        else:
+            K = tp.split_sizes(K, world, 64)[0][rank]
+    return K, N
+
+
+def build_model(spec, dev, rank, world, gen, tp_mode="nccl", ws=None, shared_scratch=None):
+    """Random-init quantized linears (per-channel) of `spec`, already sharded for `world` ranks.
+    tp_mode (world > 1): how o/down exchange — 'nccl' (plain shard, caller all-reduces), 'reduce' (multimem.red epilogue),
+    'scatter' (reduce-scatter in the epilogue + quantise/all-gather kernel; `ws` = tp.ScatterWorkspace)."""
     import qqq_b200
     from qqq_b200 import tp
 
     layers = []
-    for _ in range(MODEL["layers"]):
+    for li in range(spec["layers"]):
         mods = {}
-        for (name, k, n, mode) in LAYER_LINEARS:
-            K, N = MODEL[k], MODEL[n]
-            if world > 1:
-                if mode == "column":
-                    sizes, _ = tp.split_sizes(N, world, 64)
-                    N = sizes[rank]
-                else:
-                    sizes, _ = tp.split_sizes(K, world, 64)
-                    K = sizes[rank]
+        for (name, K0, N0, mode) in layer_linears(spec):
+            K, N = shard_dims(K0, N0, mode, rank, world)
             ql = qqq_b200.QuantLinear(4, -1, K, N, bias=False)
+            if shared_scratch is not None:  # one split-K scratch + lock array for the whole model (model.share_scratch)
+                ql.reduce_buffer = None
+                ql.workspace = None
             ql = ql.to(dev)
             ql.B = random_packed(K, N, gen, dev)
             # W8 = 16*w4 with w4 ~ U[-8,7] (std 4.6): unit-variance outputs for unit-variance inputs
-            ql.s_channel = torch.full((1, N), 1.0 / (16 * 4.6 * (MODEL[k] ** 0.5)), dtype=torch.float32, device=dev)
-            mods[name] = ql
+            ql.s_channel = torch.full((1, N), 1.0 / (16 * 4.6 * (K0 ** 0.5)), dtype=torch.float32, device=dev)
+            if shared_scratch is not None:
+                flat, locks = shared_scratch
+                ql.reduce_buffer = flat[: ql.max_par * 64 * N].view(ql.max_par * 64, N)
+                ql.workspace = locks
+            mod = ql
+            if world > 1 and mode == "row":
+                if tp_mode == "scatter":
+                    last = li == spec["layers"] - 1 and name == "down"
+                    mod = tp.ScatterRowParallelQuantLinear(ql, ws, keep_hidden=last)
+                elif tp_mode == "reduce":
+                    mod = tp.FusedRowParallelQuantLinear(ql, ws)
+            mods[name] = mod
         layers.append(mods)
     return layers
 
 
+def make_shared_scratch(spec, dev):
+    n_max = max(N for (_, _, N, _) in layer_linears(spec))
+    return (torch.zeros(16 * 64 * n_max, dtype=torch.int32, device=dev),
+            torch.zeros(max(n_max // 128 * 16, 16), dtype=torch.int32, device=dev))
+
+
 def _all_reduce_after(mod, y, world):
-    """NCCL all-reduce after a row-parallel linear — unless the module reduces in its own epilogue (--fused-allreduce)."""
+    """NCCL all-reduce after a row-parallel linear — unless the module reduces in its own epilogue (--tp-mode reduce)."""
     import torch.distributed as dist
     from qqq_b200 import tp
 
@@ -169,7 +203,7 @@ def _all_reduce_after(mod, y, world):
 
 
 def forward_chain(layers, h, world):
-    """The reference's module structure: 7 separate linears per layer (q, k, v re-quantise the same input)."""
+    """The reference's module structure: 7 separate linears per layer, called in the model's order."""
     for m in layers:
         q = m["q"](h)
         m["k"](h)
@@ -182,6 +216,25 @@ def forward_chain(layers, h, world):
         _all_reduce_after(m["down"], d, world)
         h = d
     return h
+
+
+def forward_chain_scatter(layers, x):
+    """Tensor parallel with the exchange fused into the kernels (tp.ScatterRowParallelQuantLinear): the row-parallel
+    linears return the int8 activations of their all-reduced output for all tokens, which the next column-parallel
+    linears consume directly.  Returns this rank's rows of the last layer's fp16 output (sequence-sharded)."""
+    import qqq_b200
+    from qqq_b200 import ops
+
+    qa = qqq_b200.QuantizedActivation(*ops.dynamic_quant(x))
+    for m in layers:
+        q = m["q"](qa)
+        m["k"](qa)
+        m["v"](qa)
+        qa = m["o"](q)
+        g = m["gate"](qa)
+        m["up"](qa)
+        qa = m["down"](g)
+    return layers[-1]["down"].hidden
 
 
 def merge_layers(layers):
@@ -210,14 +263,11 @@ def forward_chain_merged(mlayers, h, world):
     return h
 
 
-GEMM_NAMES = ("q", "k", "v", "o", "gate", "up", "down")
-
-
-def gemm_only_chain(mlayers, qin):
+def gemm_only_chain(layers, qin):
     """The GEMM launches of a step alone, on pre-quantised inputs (for the roofline figure of the dominant kernel)."""
     import qqq_b200
 
-    for m in mlayers:
+    for m in layers:
         for name in GEMM_NAMES:
             ql = getattr(m[name], "shard", m[name])
             A8, s1, D = qin[(ql.infeatures, ql.outfeatures)]
@@ -262,8 +312,20 @@ def graph_time_us(launch_all, n_launches, reps=3, warm=1):
     return e0.elapsed_time(e1) * 1e3 / (reps * n_launches)
 
 
-def gemm_sweep(dev, peaks, quick=False, K=8192, N=21760, Ms=(1, 16, 128, 1024, 4096)):
-    """BASELINE configs[4]: M in {1,16,128,1024,4096}, K=8192, N=21760, per-channel and g128, vs fp16 cuBLAS."""
+def load_reference_kernel():
+    """The reference's own CUDA kernel (unmodified csrc/qqq_gemm.cu built for sm_100a by oracle/build_ref.py): a COMPARATOR
+    beside our numbers, like cpu_baseline — never on the product path.  None when the build did not travel."""
+    try:
+        from oracle import build_ref
+
+        return build_ref.load()
+    except Exception:
+        return None
+
+
+def gemm_sweep(dev, peaks, quick=False, K=8192, N=21760, Ms=(1, 16, 128, 1024, 4096), ref_kernel=None):
+    """BASELINE configs[4]: M in {1,16,128,1024,4096}, K=8192, N=21760, per-channel and g128, vs fp16 cuBLAS and vs the
+    reference CUDA kernel on the same box, in the same process, with the same rotating-weights method."""
     import qqq_b200
 
     ncopy = 4  # 4 x 89 MB packed weights > 126 MB L2: every launch streams its weights from HBM
@@ -274,7 +336,7 @@ def gemm_sweep(dev, peaks, quick=False, K=8192, N=21760, Ms=(1, 16, 128, 1024, 4
     s3g = (torch.rand(K // 128, N, device=dev) * 8 + 4).half()
     s3e = torch.zeros(0, dtype=torch.float16, device=dev)
     C = torch.zeros(16 * 64, N, dtype=torch.int32, device=dev)
-    ws = torch.zeros(N // 128 * 16, dtype=torch.int32, device=dev)
+    ws = torch.zeros(N // 128 * 16 + 64, dtype=torch.int32, device=dev)
     int8_peak = 2.0 * peaks["bf16_tflops"]  # burst figure: each GEMM is timed on its own
     out = []
     for M in (Ms if not quick else (16, 1024)):
@@ -300,10 +362,23 @@ def gemm_sweep(dev, peaks, quick=False, K=8192, N=21760, Ms=(1, 16, 128, 1024, 4
             by = M * K + K * N / 2 + 2 * M * N + 4 * M + 4 * N + (2 * (K // 128) * N if mode == "g128" else 0)
             hbm_frac = by / (t * 1e-6) / 1e9 / peaks["hbm_gbs"]
             tc_frac = fl / (t * 1e-6) / 1e12 / int8_peak
-            out.append(dict(M=M, K=K, N=N, mode=mode, us=round(t, 2), tflops=round(fl / t * 1e-6, 1),
-                            gbps=round(by / t * 1e-3, 1), fp16_cublas_us=round(t_h, 2),
-                            speedup_vs_fp16=round(t_h / t, 3), bound="hbm" if hbm_frac > tc_frac else "tensor",
-                            roofline_frac=round(max(hbm_frac, tc_frac), 3)))
+            row = dict(M=M, K=K, N=N, mode=mode, us=round(t, 2), tflops=round(fl / t * 1e-6, 1),
+                       gbps=round(by / t * 1e-3, 1), fp16_cublas_us=round(t_h, 2),
+                       speedup_vs_fp16=round(t_h / t, 3), bound="hbm" if hbm_frac > tc_frac else "tensor",
+                       roofline_frac=round(max(hbm_frac, tc_frac), 3),
+                       frac_of_measured_umma_peak=round(fl / t * 1e-6 / UMMA_I8_PEAK_TOPS, 3))
+            if ref_kernel is not None:
+                try:
+                    def run_r():
+                        for i in range(ncopy):
+                            ref_kernel.qqq_gemm(A, Bs[i], C, D, s1, s2, s3, ws, -1, -1, -1, 16)
+
+                    t_r = graph_time_us(run_r, ncopy, max(1, reps // 2))
+                    row.update(ref_kernel_us=round(t_r, 2), speedup_vs_ref_kernel=round(t_r / t, 3),
+                               ref_kernel_speedup_vs_fp16=round(t_h / t_r, 3))
+                except Exception as e:  # the comparator must never cost the row
+                    row.update(ref_kernel_error=repr(e)[:120])
+            out.append(row)
     return out
 
 
@@ -311,21 +386,22 @@ def gemm_sweep(dev, peaks, quick=False, K=8192, N=21760, Ms=(1, 16, 128, 1024, 4
 # CPU path (oracle port): dequant-to-fp16 torch.matmul on host cores
 # ----------------------------------------------------------------------------------------------------------
 def cpu_layer_setup(seed=0):
-    """One decoder layer's 7 linears: packed weights -> fp16 (untimed, one-off), int8 activations + scales."""
+    """One decoder layer's 7 linears: packed weights -> fp16 (one-off, timed separately), int8 activations + scales."""
     from oracle import qqq_oracle as O
 
     rng = np.random.default_rng(seed)
     M = MODEL["seq"] * MODEL["batch"]
-    items = []
-    for (name, k, n, _) in LAYER_LINEARS:
-        K, N = MODEL[k], MODEL[n]
+    items, t_deq = [], 0.0
+    for (name, K, N, _) in layer_linears(MODEL):
         B = rng.integers(-2**31, 2**31 - 1, size=(K // 16, 2 * N), dtype=np.int64).astype(np.int32)
         s2 = np.full((1, N), 1.0 / (16 * 4.6 * K ** 0.5), np.float32)
+        t0 = time.perf_counter()
         W = torch.from_numpy(O.dequant_weights_fp16(B, s2, None))
+        t_deq += time.perf_counter() - t0
         A8 = rng.integers(-127, 128, size=(M, K), dtype=np.int64).astype(np.int8)
         s1 = np.full((M, 1), 0.03, np.float32)
         items.append((name, A8, s1, W))
-    return items
+    return items, t_deq
 
 
 def cpu_layer_run(items):
@@ -335,19 +411,29 @@ def cpu_layer_run(items):
         O.dequant_matmul_cpu(A8, s1, W.numpy())
 
 
-def cpu_baseline(steps=2, warmup=1):
+def cpu_baseline(steps=1, warmup=1, layers_per_step=None):
+    """Dequant-to-fp16 torch.matmul on the host cores.  `layers_per_step` decoder layers per timed pass (default: the
+    sample the N=1 bench line uses, 2 of 32; the --impl reference arm passes all 32)."""
     torch.set_num_threads(os.cpu_count())
-    items = cpu_layer_setup()
+    items, t_deq = cpu_layer_setup()
+    L = MODEL["layers"]
+    n = layers_per_step or 2
     for _ in range(warmup):
         cpu_layer_run(items)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_layer_run(items)
-    t = (time.perf_counter() - t0) / steps
-    tok = MODEL["seq"] * MODEL["batch"] / (t * MODEL["layers"])
+        for _ in range(n):
+            cpu_layer_run(items)
+    t_pass = (time.perf_counter() - t0) / steps  # n layers
+    t_step = t_pass * L / n
+    M = MODEL["seq"] * MODEL["batch"]
+    tok = M / t_step
     return dict(value=round(tok, 3), unit="tokens/s", cores=os.cpu_count(), kind="port",
-                sample=f"1 of {MODEL['layers']} decoder layers (7 linears, M=1024) dequant-to-fp16 torch.matmul, "
-                       f"weights pre-dequantised; {steps} timed passes, extrapolated x{MODEL['layers']}"), t
+                sample=f"{n} of {L} decoder layers per timed pass (7 linears each, M=1024) dequant-to-fp16 torch.matmul, weights "
+                       f"pre-dequantised; {steps} timed passes" + ("" if n == L else f", extrapolated x{L / n:g}"),
+                extrapolated=(n != L), ms_per_step=round(t_step * 1e3, 2),
+                dequant_ms_per_layer=round(t_deq * 1e3, 1),
+                value_including_dequant_once=round(M / (t_step + t_deq * L), 3)), t_step
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -393,10 +479,15 @@ def decode_g128(dev, peaks, steps, warmup):
 
     x = torch.randn(M, cfg["hidden"], device=dev, generator=gen).half()
     none = lambda: None  # noqa: E731
-    g = qgraph.capture(chain, x)
+    qqq_b200.set_act_quant_cache(True)
+    try:
+        g = qgraph.capture(chain, x)
+    finally:
+        qqq_b200.set_act_quant_cache(False)
     ms = timed(lambda: g(x), steps, warmup, none)
-    out = dict(workload="llama-3-8b decode batch=32 seq=1: all 224 quantized linears, per-group g=128, 7 x (act-quant + GEMM) "
-                        "per layer; random-init weights; 3.6 GB of packed weights + group scales stream from HBM every step",
+    out = dict(workload="llama-3-8b decode batch=32 seq=1: all 224 quantized linears, per-group g=128, module by module (4 "
+                        "act-quants + 7 GEMMs per layer); random-init weights; 3.6 GB of packed weights + group scales stream "
+                        "from HBM every step",
                ms_per_step=round(ms, 4), value=round(M / (ms * 1e-3), 1), unit="tokens/s",
                gbps=round(by / (ms * 1e-3) / 1e9, 1), hbm_frac=round(by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 3),
                algorithmic_bytes_per_step=by)
@@ -414,7 +505,8 @@ def decode_g128(dev, peaks, steps, warmup):
 
     gm = qgraph.capture(chain_merged, x)
     ms_m = timed(lambda: gm(x), steps, warmup, none)
-    out["merged"] = dict(ms_per_step=round(ms_m, 4), value=round(M / (ms_m * 1e-3), 1))
+    out["merged"] = dict(ms_per_step=round(ms_m, 4), value=round(M / (ms_m * 1e-3), 1),
+                         hbm_frac=round(by / (ms_m * 1e-3) / 1e9 / peaks["hbm_gbs"], 3))
     return out
 
 
@@ -468,6 +560,173 @@ def full_forward(dev, steps, warmup):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# tensor parallel extras (N > 1): parity leg, GEMM sweep split-N / split-K, Llama-2-70B (configs[3])
+# ----------------------------------------------------------------------------------------------------------
+TP_PARITY_CASES = (("pc_m1024_k4096_n4096", 1024, 4096, 4096, -1), ("g128_m48_k4096_n2048", 48, 4096, 2048, 128))
+
+
+def tp_parity(dev, rank, world, ws):
+    """Untimed correctness leg carried by every multi-GPU line: on real shapes, with the same random weights on every rank,
+      column: this rank's column shard == the 1-GPU module's columns, bit for bit;
+      scatter: the fused exchange == its torch restatement on the ranks' partial outputs, bit for bit (int8, scales, fp16
+               rows), and its fp16 sum vs the 1-GPU output within tolerance (per-shard activation scales differ by design);
+      nccl:   plain shard + NCCL fp16 all-reduce vs the 1-GPU output within tolerance;
+      exact:  shared-scale int32 mode == the 1-GPU module, bit for bit."""
+    import torch.distributed as dist
+
+    import qqq_b200
+    from qqq_b200 import tp
+
+    res = {}
+    for (label, M, K, N, gs) in TP_PARITY_CASES:
+        gen = torch.Generator(device=dev).manual_seed(777)  # same seed on every rank: identical full module
+        full = qqq_b200.QuantLinear(4, gs, K, N, bias=False).to(dev)
+        full.B = random_packed(K, N, gen, dev)
+        full.s_channel = (torch.rand(1, N, device=dev, generator=gen) + 0.5) / (16 * 4.6 * K ** 0.5)
+        if gs == 128:
+            full.s_group = (torch.rand(K // 128, N, device=dev, generator=gen) * 8 + 4).half()
+        x = torch.randn(M, K, device=dev, generator=gen).half()
+        y_one = full(x)
+        scale = float(y_one.float().abs().max())
+        col = tp.shard_quant_linear(full, rank, world, "column")
+        _, offs = tp.split_sizes(N, world, 64)
+        ok_col = torch.equal(col(x).view(torch.int16), y_one[:, offs[rank]:offs[rank + 1]].contiguous().view(torch.int16))
+        row = tp.shard_quant_linear(full, rank, world, "row")
+        _, koffs = tp.split_sizes(K, world, 128 if gs != -1 else 64)
+        x_loc = x[:, koffs[rank]:koffs[rank + 1]].contiguous()
+        part = row(x_loc)
+        parts = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(parts, part)
+        h_ref, a8_ref, s1_ref = tp.reference_reduce_quant(parts)
+        r = dict(column_bit_equal=bool(ok_col))
+        if ws is not None:
+            mod = tp.ScatterRowParallelQuantLinear(row, ws, keep_hidden=True)
+            qa = mod(x_loc)
+            torch.cuda.synchronize()
+            rows = -(-M // world)
+            mine = slice(rank * rows, min(M, (rank + 1) * rows))
+            r["scatter_bit_equal_to_restatement"] = bool(
+                torch.equal(qa.q, a8_ref) and torch.equal(qa.s1.view(torch.int32), s1_ref.view(torch.int32))
+                and torch.equal(mod.hidden.view(torch.int16), h_ref[mine].view(torch.int16)))
+            r["scatter_timeouts"] = ws.timeouts()
+        r["row_sum_max_rel_err_vs_1gpu"] = round(float((h_ref.float() - y_one.float()).abs().max()) / max(scale, 1e-9), 5)
+        y_nccl = tp.RowParallelQuantLinear(row)(x_loc)
+        r["nccl_max_rel_err_vs_1gpu"] = round(float((y_nccl.float() - y_one.float()).abs().max()) / max(scale, 1e-9), 5)
+        y_exact = tp.ExactRowParallelQuantLinear(row)(x_loc)
+        r["exact_bit_equal"] = bool(torch.equal(y_exact.view(torch.int16), y_one.view(torch.int16)))
+        flags = torch.tensor([int(r["column_bit_equal"]), int(r.get("scatter_bit_equal_to_restatement", True)),
+                              int(r["exact_bit_equal"]), int(r.get("scatter_timeouts", 0) == 0)], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)  # every rank must agree
+        r["all_ranks"] = bool(int(flags.min().item()) == 1)
+        r["tolerance"] = "row-parallel sums use per-shard activation scales: |err| <= 3e-2 * max|y| (tests/test_tp_gloo.py)"
+        r["within_tolerance"] = bool(r["row_sum_max_rel_err_vs_1gpu"] <= 3e-2 and r["nccl_max_rel_err_vs_1gpu"] <= 3e-2)
+        res[label] = r
+    res["green"] = all(v["all_ranks"] and v["within_tolerance"] for v in res.values())
+    return res
+
+
+def gemm_sweep_tp(dev, peaks, rank, world, ws, max_over_ranks, K=8192, N=21760, Ms=(16, 1024)):
+    """North star: the sweep shape at TP = world, split N (no collective) and split K (+ the exchange), separately.
+    Times are per launch (max over ranks); TFLOP/s is the whole job's 2*M*K*N over that time."""
+    import torch.distributed as dist
+
+    import qqq_b200
+    from qqq_b200 import ops, tp
+
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    out = []
+    n_loc = tp.split_sizes(N, world, 64)[0][rank]
+    k_loc = tp.split_sizes(K, world, 128)[0][rank]
+    int8_peak = 2.0 * peaks["bf16_tflops"]
+    for mode in ("per-channel", "g128"):
+        for split, (Kr, Nr) in (("N", (K, n_loc)), ("K", (k_loc, N))):
+            ncopy = min(24, max(4, int(300e6 // (Kr * Nr // 2)) + 1))  # rotating weights: more than L2 per rank
+            Bs = [random_packed(Kr, Nr, g, dev) for _ in range(ncopy)]
+            mods = []
+            for B in Bs:
+                ql = qqq_b200.QuantLinear(4, 128 if mode == "g128" else -1, Kr, Nr, bias=False).to(dev)
+                ql.B = B
+                ql.s_channel = torch.rand(1, Nr, device=dev) * 1e-3 + 5e-4
+                if mode == "g128":
+                    ql.s_group = (torch.rand(Kr // 128, Nr, device=dev) * 8 + 4).half()
+                mods.append(ql)
+            for i in range(1, ncopy):  # one scratch for all copies
+                mods[i].reduce_buffer, mods[i].workspace = mods[0].reduce_buffer, mods[0].workspace
+            for M in Ms:
+                A = torch.randint(-127, 128, (M, Kr), dtype=torch.int8, device=dev)
+                s1 = torch.rand(M, 1, device=dev) * 1e-2 + 1e-3
+                qa = qqq_b200.QuantizedActivation(A, s1)
+                fl = 2.0 * M * K * N
+                row = dict(M=M, K=K, N=N, mode=mode, split=split, tp=world)
+                variants = [("gemm_only", lambda: [m(qa) for m in mods])]
+                if split == "K":
+                    if ws is not None and M <= ws.max_tokens and N <= ws.max_features:
+                        smods = [tp.ScatterRowParallelQuantLinear(m, ws) for m in mods]
+                        variants.append(("fused_exchange", lambda: [m(qa) for m in smods]))
+
+                    def run_nccl():
+                        for m in mods:
+                            dist.all_reduce(m(qa))
+
+                    variants.append(("nccl_allreduce", run_nccl))
+                for vname, fn in variants:
+                    dist.barrier()
+                    t = max_over_ranks(graph_time_us(fn, ncopy, 3 if M <= 1024 else 1) * 1e-3) * 1e3
+                    row[vname + "_us"] = round(t, 2)
+                    row[vname + "_tflops"] = round(fl / t * 1e-6, 1)
+                t0 = row["gemm_only_us"]
+                by = (M * Kr + Kr * Nr / 2 + 2 * M * Nr + 4 * M + 4 * Nr + (2 * (Kr // 128) * Nr if mode == "g128" else 0))
+                hbm_frac = by / (t0 * 1e-6) / 1e9 / peaks["hbm_gbs"]
+                tc_frac = (fl / world) / (t0 * 1e-6) / 1e12 / int8_peak
+                row.update(bound="hbm" if hbm_frac > tc_frac else "tensor", roofline_frac_per_gpu=round(max(hbm_frac, tc_frac), 3))
+                if split == "K" and "fused_exchange_us" in row:
+                    # bytes this GPU must send (reduce-scatter of fp16) and receive (all-gather of int8) over NVLink
+                    nv_out = (world - 1) / world * M * N * 2
+                    nv_in = (world - 1) / world * M * N * 1
+                    row["nvlink_bytes_out_in"] = [int(nv_out), int(nv_in)]
+                    row["fused_exchange_nvlink_gbs"] = round(nv_out / ((row["fused_exchange_us"]) * 1e-6) / 1e9, 1)
+                out.append(row)
+            del Bs, mods
+            torch.cuda.empty_cache()
+    return out
+
+
+def model_tp_section(spec, dev, rank, world, ws_factory, steps, warmup, barrier, max_over_ranks, tp_mode):
+    """A whole model's quantized linears at TP = world (configs[3]: Llama-2-70B, TP=8): tokens/s of the same chain as the
+    headline, max over ranks."""
+    import qqq_b200
+    from qqq_b200 import graph as qgraph
+
+    M = spec["seq"] * spec["batch"]
+    gen = torch.Generator(device=dev).manual_seed(4242 + rank)
+    ws = ws_factory(M, spec["hidden"]) if tp_mode in ("scatter", "reduce") else None
+    layers = build_model(spec, dev, rank, world, gen, tp_mode, ws, shared_scratch=make_shared_scratch(spec, dev))
+    x = torch.randn(M, spec["hidden"], device=dev, generator=gen).half()
+    if tp_mode == "scatter":
+        fn = lambda t: forward_chain_scatter(layers, t)  # noqa: E731
+    else:
+        fn = lambda t: forward_chain(layers, t, world)  # noqa: E731
+    qqq_b200.set_act_quant_cache(True)
+    try:
+        l0 = qqq_b200.launch_count()
+        fn(x)
+        n_l = qqq_b200.launch_count() - l0
+        gr = qgraph.capture(fn, x)
+    finally:
+        qqq_b200.set_act_quant_cache(False)
+    ms = max_over_ranks(timed(lambda: gr(x), steps, warmup, barrier))
+    fl = model_flops(spec, M)
+    res = dict(workload=f"{spec['name']} prefill seq={spec['seq']} batch={spec['batch']}: all {7 * spec['layers']} quantized "
+                        f"linears per-channel W4A8, tensor parallel = {world} ({tp_mode}); random-init weights",
+               ms_per_step=round(ms, 4), value=round(M / (ms * 1e-3), 1), unit="tokens/s", gpu_launches_per_step=int(n_l),
+               tflops=round(fl / (ms * 1e-3) / 1e12, 1),
+               frac_of_int8_roof_per_gpu=round(fl / world / (ms * 1e-3) / 1e12 / (2.0 * load_peaks()["bf16_tflops"]), 3))
+    if ws is not None and hasattr(ws, "timeouts"):
+        res["exchange_timeouts"] = ws.timeouts()
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,17 +736,23 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-merged", action="store_true", help="skip the merged QKV / gate-up variant (profiler runs)")
-    ap.add_argument("--fused-allreduce", action="store_true",
-                    help="N > 1: row-parallel linears reduce in their own epilogue (tp.FusedRowParallelQuantLinear)")
+    ap.add_argument("--tp-mode", default="scatter", choices=["scatter", "nccl", "reduce"],
+                    help="N > 1: how the row-parallel linears exchange (see the module docstring)")
+    ap.add_argument("--fused-allreduce", action="store_true", help="alias of --tp-mode reduce")
     ap.add_argument("--no-decode", action="store_true", help="skip the Llama-3-8B g128 decode section (configs[2])")
     ap.add_argument("--no-full", action="store_true", help="skip the whole-model (HF Llama forward) section")
+    ap.add_argument("--no-70b", action="store_true", help="N > 1: skip the Llama-2-70B section (configs[3])")
+    ap.add_argument("--no-tp-sweep", action="store_true", help="N > 1: skip the tensor-parallel GEMM sweep")
     ap.add_argument("--aux-budget", type=float, default=300.0, help="seconds the auxiliary sections may take in total")
     args = ap.parse_args()
+    if args.fused_allreduce:
+        args.tp_mode = "reduce"
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
     M = MODEL["seq"] * MODEL["batch"]
     cfg = dict(workload="llama-2-7b prefill seq=1024 batch=1: all 224 quantized linears (per-channel W4A8), called module "
-                        "by module as the reference model does: per layer 7 x (per-token act-quant + W4A8 GEMM); "
+                        "by module in the reference model's order: per layer 7 W4A8 GEMMs + 4 per-token activation quants "
+                        "(q/k/v and gate/up share the quantisation of their common input; bit-identical to 7 + 7); "
                         "random-init weights",
                global_batch=MODEL["batch"], seq_len=MODEL["seq"], parallelism=f"tp{world}" if world > 1 else "single",
                l2="inputs larger than L2: 3.2 GB of packed weights stream from HBM every step")
@@ -495,12 +760,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        base, t_layer = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
-        ms = t_layer * MODEL["layers"] * 1e3
+        base, t_step = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)),
+                                    layers_per_step=MODEL["layers"])
         line = dict(impl="reference", metric="llama2_7b_w4a8_prefill_linears_tokens_per_s", value=base["value"],
-                    unit="tokens/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms, 2),
-                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f16", data="synthetic",
-                    config=cfg, cpu_baseline=base,
+                    unit="tokens/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=round(t_step * 1e3, 2), higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="f16", data="synthetic", config=cfg, cpu_baseline=base,
                     e2e=dict(value=base["value"], unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return 0
@@ -519,23 +784,6 @@ def main():
     else:
         barrier = lambda: None  # noqa: E731
     peaks = load_peaks()
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    layers = build_model(dev, rank, world, gen)
-    if args.fused_allreduce and world > 1:
-        # o_proj / down_proj add their output tiles into a multicast buffer from the GEMM epilogue (multimem.red over
-        # NVSwitch) instead of being followed by an NCCL all-reduce
-        from qqq_b200 import tp
-
-        ar_ws = tp.AllReduceWorkspace(M, MODEL["hidden"], device=torch.device(dev))
-        for m in layers:
-            m["o"] = tp.FusedRowParallelQuantLinear(m["o"], ar_ws)
-            m["down"] = tp.FusedRowParallelQuantLinear(m["down"], ar_ws)
-        cfg["parallelism"] += " (all-reduce fused into the GEMM epilogue, multimem.red)"
-    x_host = (torch.randn(M, MODEL["hidden"], generator=torch.Generator().manual_seed(7))).half().pin_memory()
-    out_host = torch.empty(M, MODEL["hidden"], dtype=torch.float16).pin_memory()
-    x_dev = x_host.to(dev)
-
-    # --- device-resident throughput (value): a step's launches are replayed from one CUDA graph ---
     from qqq_b200 import graph as qgraph
 
     def max_over_ranks(ms_local):
@@ -544,38 +792,81 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # headline: the 224 linears called module by module like the reference model (7 activation quants + 7 GEMMs per layer)
+    # --- tensor-parallel plumbing: exchange workspace, parity leg (untimed), fallback to NCCL if the fabric lacks it ---
+    tp_mode = args.tp_mode if world > 1 else "single"
+    tp_note, parity, ws = None, None, None
+
+    def ws_factory(m_tok, feat):
+        from qqq_b200 import tp
+
+        if tp_mode == "scatter":
+            return tp.ScatterWorkspace(m_tok, feat, device=torch.device(dev))
+        return tp.AllReduceWorkspace(m_tok, feat, device=torch.device(dev))
+
+    if world > 1:
+        if tp_mode in ("scatter", "reduce"):
+            try:
+                ws = ws_factory(max([M] + [c[1] for c in TP_PARITY_CASES]), max([MODEL["hidden"]] + [c[3] for c in TP_PARITY_CASES]))
+            except Exception as e:  # no symmetric memory / multicast on this box: the NCCL path still works
+                tp_note = f"--tp-mode {tp_mode} unavailable ({repr(e)[:160]}); fell back to nccl"
+                tp_mode = "nccl"
+        try:
+            parity = tp_parity(dev, rank, world, ws if tp_mode == "scatter" else None)
+        except Exception as e:
+            parity = {"error": repr(e)[:300], "green": False}
+        if tp_mode == "scatter" and not parity.get("green", False):
+            tp_note = "fused exchange failed its parity leg; fell back to nccl"
+            tp_mode, ws = "nccl", None
+        cfg["parallelism"] = f"tp{world}: q,k,v,gate,up split N; o,down split K, exchange = " + {
+            "scatter": "reduce-scatter in the GEMM epilogue (peer stores) + per-token quant / int8 all-gather kernel (multicast)",
+            "reduce": "one-shot all-reduce in the GEMM epilogue (multimem.red)",
+            "nccl": "NCCL all-reduce of the fp16 output"}[tp_mode]
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    layers = build_model(MODEL, dev, rank, world, gen, tp_mode, ws)
+    x_host = (torch.randn(M, MODEL["hidden"], generator=torch.Generator().manual_seed(7))).half().pin_memory()
+    x_dev = x_host.to(dev)
+    if tp_mode == "scatter":
+        chain = lambda x: forward_chain_scatter(layers, x)  # noqa: E731
+    else:
+        chain = lambda x: forward_chain(layers, x, world)  # noqa: E731
+
+    # --- device-resident throughput (value): a step's launches are replayed from one CUDA graph ---
+    qqq_b200.set_act_quant_cache(True)
     l0 = qqq_b200.launch_count()
-    forward_chain(layers, x_dev, world)
+    y0 = chain(x_dev)
     launches_per_step = qqq_b200.launch_count() - l0
-    graphed = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
+    out_host = torch.empty(tuple(y0.shape), dtype=torch.float16).pin_memory()
+    graphed = qgraph.capture(chain, x_dev)
+    qqq_b200.set_act_quant_cache(False)
     with ClockSampler(local_rank) as cs:
         ms = max_over_ranks(timed(lambda: graphed(x_dev), args.steps, args.warmup, barrier))
     value = M / (ms * 1e-3)
-    # the same weights with q/k/v and gate/up merged (SURVEY row N1): 4 activation quants + 4 GEMMs per layer
-    ms_mrg = None
-    if not args.no_merged:
-        mlayers = merge_layers(layers)
-        graphed_mrg = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
-        ms_mrg = max_over_ranks(timed(lambda: graphed_mrg(x_dev), args.steps, args.warmup, barrier))
-        del graphed_mrg, mlayers
+
     # --- end to end: pinned host input -> H2D -> 224 linears -> D2H of the result, every step ---
     def e2e_step():
         h = graphed(x_host)  # pinned host -> static device input (H2D), graph replay
-        out_host.copy_(h, non_blocking=True)  # D2H of the step's result
+        out_host.copy_(h, non_blocking=True)  # D2H of the step's result (N > 1: this rank's rows / replica)
+
+    ms_e2e = max_over_ranks(timed(e2e_step, args.steps, args.warmup, barrier))
 
     # the same step through the eager public API (no graph), for the record
     def eager_step():
         x_dev.copy_(x_host, non_blocking=True)
-        out_host.copy_(forward_chain(layers, x_dev, world), non_blocking=True)
+        out_host.copy_(chain(x_dev), non_blocking=True)
 
+    qqq_b200.set_act_quant_cache(True)
     ms_eager = timed(eager_step, args.steps, args.warmup, barrier)
+    qqq_b200.set_act_quant_cache(False)
+    exchange_timeouts = ws.timeouts() if (ws is not None and hasattr(ws, "timeouts")) else None
 
-    ms_e2e = timed(e2e_step, args.steps, args.warmup, barrier)
-    t = torch.tensor([ms_e2e], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    # the same weights with q/k/v and gate/up merged (SURVEY row N1): 4 activation quants + 4 GEMMs per layer
+    ms_mrg = None
+    if not args.no_merged and tp_mode in ("single", "nccl"):
+        mlayers = merge_layers(layers)
+        graphed_mrg = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
+        ms_mrg = max_over_ranks(timed(lambda: graphed_mrg(x_dev), args.steps, args.warmup, barrier))
+        del graphed_mrg, mlayers
 
     # --- dominant kernel alone: the 224 GEMM launches on pre-quantised inputs ---
     qin = {}
@@ -585,106 +876,125 @@ def main():
         if key not in qin:
             A8 = torch.randint(-127, 128, (M, key[0]), dtype=torch.int8, device=dev)
             qin[key] = (A8, torch.full((M, 1), 0.03, device=dev), torch.empty(M, key[1], dtype=torch.float16, device=dev))
+
     def _gemm_chain(x):
         gemm_only_chain(layers, qin)
         return x
 
     graphed_gemm = qgraph.capture(_gemm_chain, x_dev)
-    ms_gemm = timed(lambda: graphed_gemm(x_dev), args.steps, args.warmup, barrier)
+    ms_gemm = max_over_ranks(timed(lambda: graphed_gemm(x_dev), args.steps, args.warmup, barrier))
     n_gemm = MODEL["layers"] * len(GEMM_NAMES)
-    flops_rank = model_flops(M) / world
-    int8_peak = 2.0 * peaks["bf16_tflops_sustained"]
+    flops_rank = model_flops(MODEL, M) / world
+    # the timed region is a fraction of a second at boost clocks: the burst figure is the right denominator
+    int8_peak = 2.0 * peaks["bf16_tflops"]
     achieved = flops_rank / (ms_gemm * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01", "final", "ncu", "traffic.json")
+    traffic, tnote = None, "not captured for this configuration"
+    tpath = os.path.join(ROOT, "profiles", "r02", "ncu", "traffic.json")
     if world == 1 and os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full captures
         traffic = json.load(open(tpath)).get("llama2_7b_prefill_m1024", {}).get("avg_per_launch")
+        tnote = ("dram__bytes_read+write per launch, mean over the 7 GEMMs of a layer, from the committed ncu --set full "
+                 "captures (profiles/r02/ncu/traffic.json), not measured in this run")
     roofline = dict(bound="tensor", kernel="qqq_gemm_kernel<per-channel> (tcgen05 kind::i8)", achieved=round(achieved, 1),
                     peak=round(int8_peak, 1), unit="TFLOP/s", frac=round(achieved / int8_peak, 4), traffic=traffic,
-                    traffic_note="dram__bytes_read+write per launch, mean over the 7 GEMMs of a layer (ncu, "
-                                 "profiles/r01/final/ncu/traffic.json); below the algorithmic bytes because A8 and D stay in L2",
-                    peak_source=f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['source']}); int8 dense = 2x bf16 "
-                                "on sm_100a; UTCIMMA-only microbenchmark on this pool measured 4428 TOP/s burst "
-                                "(profiles/r01/probe_umma_i8.log)",
-                    frac_of_burst_umma_i8_peak=round(achieved / 4428.0, 4),  # the stricter, clock-unthrottled denominator
+                    traffic_note=tnote,
+                    peak_source=f"2 x bf16_tflops (burst) of MEASURED_PEAKS.json ({peaks['source']}); int8 dense = 2x bf16 on "
+                                "sm_100a",
+                    frac_of_sustained=round(achieved / (2.0 * peaks["bf16_tflops_sustained"]), 4),
+                    frac_of_measured_umma_peak=round(achieved / UMMA_I8_PEAK_TOPS, 4),
                     launches=n_gemm, avg_launch_us=round(ms_gemm * 1e3 / n_gemm, 2),
-                    algorithmic_flops_per_step=flops_rank, algorithmic_bytes_per_step=model_gemm_bytes(M) / world)
+                    algorithmic_flops_per_step=flops_rank, algorithmic_bytes_per_step=model_gemm_bytes(MODEL, M) / world)
 
-    line = None
-    if rank == 0:
-        line = dict(metric="llama2_7b_w4a8_prefill_linears_tokens_per_s", value=round(value, 1), unit="tokens/s",
-                    n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms, 4), higher_is_better=True,
-                    scaling="strong", vs_baseline=None, dtype="int8", data="synthetic", config=cfg,
-                    clocks=cs.summary(),
-                    e2e=dict(value=round(M / (ms_e2e * 1e-3), 1), unit="tokens/s", ms_per_step=round(ms_e2e, 4),
-                             h2d_bytes_per_step=x_host.numel() * 2, d2h_bytes_per_step=out_host.numel() * 2,
-                             api="qqq_b200.graph.capture(QuantLinear chain); eager QuantLinear.forward loop: "
-                                 f"{ms_eager:.3f} ms/step"),
-                    gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
-                    launch_mode="cuda-graph replay of the per-step launches",
-                    merged=None if ms_mrg is None else dict(
-                        ms_per_step=round(ms_mrg, 4), value=round(M / (ms_mrg * 1e-3), 1),
-                        note="same weights with q/k/v and gate/up merged by concatenating their packed tensors "
-                             "(qqq_b200.merge_quant_linears, bit-identical outputs): 4 act-quants + 4 GEMMs per layer"),
-                    roofline=roofline, tflops_linears=round(flops_rank * world / (ms * 1e-3) / 1e12, 1))
-        # Auxiliary sections: each guarded, all under one watchdog, so that neither an exception nor a stall in them
-        # can cost the headline line above.
-        aux = []
-        if world == 1 and not args.no_cpu:  # first: the contract's cpu_baseline must not fall to the watchdog
-            aux.append(("cpu_baseline", lambda: cpu_baseline()[0]))
-        if world == 1 and not args.no_sweep:
-            aux.append(("gemm_sweep", lambda: gemm_sweep(dev, peaks)))
-        def shared_act_quant():
-            # the headline's 7-module structure with the opt-in activation-quant cache: q/k/v and gate/up quantise their
-            # shared input once (bit-identical outputs; 4 act-quants + 7 GEMMs per layer)
-            qqq_b200.set_act_quant_cache(True)
-            try:
-                l1 = qqq_b200.launch_count()
-                forward_chain(layers, x_dev, world)
-                n_l = qqq_b200.launch_count() - l1
-                gr = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
-                ms_c = timed(lambda: gr(x_dev), args.steps, args.warmup, barrier)
-            finally:
-                qqq_b200.set_act_quant_cache(False)
-            return dict(ms_per_step=round(ms_c, 4), value=round(M / (ms_c * 1e-3), 1), gpu_launches_per_step=int(n_l),
-                        note="qqq_b200.set_act_quant_cache(True): same modules and call order as the headline")
+    line = dict(metric="llama2_7b_w4a8_prefill_linears_tokens_per_s", value=round(value, 1), unit="tokens/s",
+                n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(ms, 4), higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="int8", data="synthetic", config=cfg,
+                clocks=cs.summary(),
+                e2e=dict(value=round(M / (ms_e2e * 1e-3), 1), unit="tokens/s", ms_per_step=round(ms_e2e, 4),
+                         h2d_bytes_per_step=x_host.numel() * 2, d2h_bytes_per_step=out_host.numel() * 2,
+                         api="qqq_b200.graph.capture(QuantLinear chain); eager QuantLinear.forward loop: "
+                             f"{ms_eager:.3f} ms/step"),
+                gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
+                launch_mode="cuda-graph replay of the per-step launches",
+                merged=None if ms_mrg is None else dict(
+                    ms_per_step=round(ms_mrg, 4), value=round(M / (ms_mrg * 1e-3), 1),
+                    note="same weights with q/k/v and gate/up merged by concatenating their packed tensors "
+                         "(qqq_b200.merge_quant_linears, bit-identical outputs): 4 act-quants + 4 GEMMs per layer"),
+                roofline=roofline, tflops_linears=round(flops_rank * world / (ms * 1e-3) / 1e12, 1))
+    if world > 1:
+        line["tp_mode"] = tp_mode
+        line["tp_parity"] = parity
+        if tp_note:
+            line["tp_note"] = tp_note
+        if exchange_timeouts is not None:
+            line["exchange_timeouts"] = exchange_timeouts
 
-        if world == 1 and not args.no_merged:
-            aux.append(("shared_act_quant", shared_act_quant))
-        if world == 1 and not args.no_decode:
-            aux.append(("decode_g128", lambda: decode_g128(dev, peaks, args.steps, args.warmup)))
+    # Auxiliary sections: each guarded, all under one watchdog, so that neither an exception nor a stall in them
+    # can cost the headline line above.  At N > 1 every rank runs them (they contain collectives); rank 0 prints.
+    aux = []
+    if world == 1 and not args.no_cpu:  # first: the contract's cpu_baseline must not fall to the watchdog
+        aux.append(("cpu_baseline", lambda: cpu_baseline()[0]))
+    if world == 1 and not args.no_sweep:
+        aux.append(("gemm_sweep", lambda: gemm_sweep(dev, peaks, ref_kernel=load_reference_kernel())))
 
-        if world == 1 and not args.no_full:
-            aux.append(("full_forward", lambda: full_forward(dev, args.steps, args.warmup)))
-        if world == 1 and not args.no_sweep:  # the sweep shape once transposed (K=21760, N=8192); last
-            aux.append(("gemm_sweep_transposed", lambda: gemm_sweep(dev, peaks, K=21760, N=8192, Ms=(16, 1024))))
+    def per_module_quant():
+        # the reference's literal structure: every linear quantises its own input (7 act-quants + 7 GEMMs per layer)
+        l1 = qqq_b200.launch_count()
+        forward_chain(layers, x_dev, world)
+        n_l = qqq_b200.launch_count() - l1
+        gr = qgraph.capture(lambda x: forward_chain(layers, x, world), x_dev)
+        ms_c = timed(lambda: gr(x_dev), args.steps, args.warmup, barrier)
+        return dict(ms_per_step=round(ms_c, 4), value=round(M / (ms_c * 1e-3), 1), gpu_launches_per_step=int(n_l),
+                    note="activation-quant cache off: 7 act-quants + 7 GEMMs per layer, the round-1 headline structure")
 
-        def emit_and_exit():
+    if world == 1 and not args.no_merged:
+        aux.append(("per_module_quant", per_module_quant))
+    if world == 1 and not args.no_decode:
+        aux.append(("decode_g128", lambda: decode_g128(dev, peaks, args.steps, args.warmup)))
+    if world == 1 and not args.no_full:
+        aux.append(("full_forward", lambda: full_forward(dev, args.steps, args.warmup)))
+    if world == 1 and not args.no_sweep:  # the sweep shape once transposed (K=21760, N=8192); last
+        aux.append(("gemm_sweep_transposed", lambda: gemm_sweep(dev, peaks, K=21760, N=8192, Ms=(16, 1024),
+                                                                  ref_kernel=load_reference_kernel())))
+    if world > 1 and not args.no_tp_sweep:
+        aux.append(("gemm_sweep_tp", lambda: gemm_sweep_tp(dev, peaks, rank, world, ws if tp_mode == "scatter" else None,
+                                                           max_over_ranks)))
+    if world > 1 and not args.no_70b:
+        aux.append(("llama2_70b_tp", lambda: model_tp_section(LLAMA2_70B, dev, rank, world, ws_factory, args.steps,
+                                                              args.warmup, barrier, max_over_ranks, tp_mode)))
+
+    def emit_and_exit():
+        if rank == 0:
             line["aux_timeout_s"] = args.aux_budget
             try:
                 print(json.dumps(line))
             except Exception:
                 print(json.dumps({k: v for k, v in list(line.items()) if k not in dict(aux)}))
             sys.stdout.flush()
-            os._exit(0)
+        os._exit(0)
 
-        wd = threading.Timer(args.aux_budget, emit_and_exit)
-        wd.daemon = True
-        wd.start()
-        for key, fn in aux:
-            try:
-                line[key] = fn()
-            except Exception as e:  # reported, never fatal
-                line[key] = {"error": repr(e)[:300]}
-        wd.cancel()
+    wd = threading.Timer(args.aux_budget, emit_and_exit)
+    wd.daemon = True
+    wd.start()
+    # the headline's graphs are no longer needed; free their pools before the auxiliary sections allocate
+    del graphed_gemm
+    for key, fn in aux:
+        try:
+            line[key] = fn()
+        except Exception as e:  # reported, never fatal
+            line[key] = {"error": repr(e)[:300]}
+            if world > 1:  # a rank that left a collective section early would deadlock the others in the next one
+                break
+    wd.cancel()
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         # CUDA graphs captured above hold references into the NCCL communicator; tearing the process group down
-        # underneath them can hang, so synchronise, flush and leave without running destructors.
-        torch.cuda.synchronize()
-        dist.barrier()
+        # underneath them can hang, so flush and leave without running destructors.
         sys.stdout.flush()
         sys.stderr.flush()
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
         os._exit(0)
     return 0
 

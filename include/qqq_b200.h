@@ -66,6 +66,33 @@ int qqq_gemm_reduce_sm100a(const void* A, const void* B, void* C, void* D_multic
                            int dev, void* stream /* cudaStream_t */, int thread_k, int thread_n, int sms, int max_par);
 
 /*
+ * Tensor-parallel row shards as a two-kernel fused exchange — reduce-scatter in the GEMM epilogue, all-gather in the
+ * quantisation of the next block's input (new work; replaces "GEMM, NCCL all-reduce, replicated
+ * activation quant").  Token rows are owned in blocks of tp_rows = ceil(M / world) rows: rank r owns [r*tp_rows, ...).
+ *
+ * qqq_gemm_scatter_sm100a: the GEMM of qqq_gemm_sm100a on this rank's K-shard; the fp16 output row m is stored into
+ *   peer_partials[m / tp_rows] + ((tp_rank * tp_rows + m % tp_rows) * N): slot `tp_rank` of the owner's partial-sum buffer
+ *   (fp16 [world][tp_rows][N], peer-mapped device pointers, e.g. torch symmetric memory's buffer_ptrs; a HOST array of
+ *   tp_world pointers, read during the call).  Scratch contract and return codes as qqq_gemm_sm100a.
+ * qqq_tp_reduce_quant_sm100a (run by every rank after its scatter GEMM, same stream): waits in-kernel until all ranks'
+ *   GEMMs have delivered, sums the world slots of its own rows in fp32 in rank order, rounds once to fp16 (+ bias), applies
+ *   the reference's per-token quantisation (qlinear_marlin.py:265-268) and writes int8 rows + fp32 scales into the gathered
+ *   buffers a8 [world*tp_rows][N] / s1 [world*tp_rows] of EVERY rank (multicast address when given, else one store per
+ *   entry of a8_dst / s1_dst), optionally its fp16 rows into h_out [tp_rows][N]; returns (stream-ordered) when all ranks'
+ *   rows have arrived here.  `flags`: 32 zero-initialised uint32 of this rank in peer-mapped memory, peer_flags[r] the same
+ *   block on rank r; flags[18] counts waits that timed out (2 s) — never a hang.  All ranks must issue the same sequence of
+ *   calls.
+ */
+int qqq_gemm_scatter_sm100a(const void* A, const void* B, void* C, void* const* peer_partials, const void* s1,
+                            const void* s2, const void* s3, int prob_m, int prob_n, int prob_k, void* workspace,
+                            int groupsize, int dev, void* stream /* cudaStream_t */, int sms, int max_par, int tp_rank,
+                            int tp_world, int tp_rows);
+int qqq_tp_reduce_quant_sm100a(const void* partials, void* const* a8_dst, void* a8_multicast, void* const* s1_dst,
+                               void* s1_multicast, void* h_out, const void* bias, void* flags, void* const* peer_flags,
+                               int tp_rank, int tp_world, int tp_rows, int prob_m, int prob_n, int dev,
+                               void* stream /* cudaStream_t */);
+
+/*
  * The same GEMM without its epilogue scales: D_int32[M,N] (int32, row-major) = A[M,K] (int8) x W8[K,N], the exact integer
  * accumulators.  For the bit-exact tensor-parallel mode of row shards: every rank quantises its K-shard
  * of the activations with the SHARED per-token scale (all-reduce-max of the row maxima), the int32 partial sums are

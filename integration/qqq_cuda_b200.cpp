@@ -28,7 +28,21 @@ void qqq_gemm(const torch::Tensor& A, const torch::Tensor& B, torch::Tensor& C, 
   TORCH_CHECK(A.scalar_type() == at::kChar && B.scalar_type() == at::kInt && C.scalar_type() == at::kInt &&
                   D.scalar_type() == at::kHalf && workspace.scalar_type() == at::kInt,
               "qqq_gemm: A int8, B/C/workspace int32, D float16 expected.");
-  TORCH_CHECK(A.is_contiguous() && B.is_contiguous() && C.is_contiguous() && D.is_contiguous(), "qqq_gemm: tensors must be contiguous.");
+  TORCH_CHECK(A.is_contiguous() && B.is_contiguous() && C.is_contiguous() && D.is_contiguous() && s1.is_contiguous() &&
+                  s2.is_contiguous() && s3.is_contiguous() && workspace.is_contiguous(),
+              "qqq_gemm: tensors must be contiguous.");
+  TORCH_CHECK(s1.is_cuda() && s2.is_cuda() && (s3.numel() == 0 || s3.is_cuda()), "qqq_gemm: scales must be CUDA tensors.");
+  for (const torch::Tensor* t : std::initializer_list<const torch::Tensor*>{&B, &C, &D, &s1, &s2, &workspace})
+    TORCH_CHECK(t->get_device() == A.get_device(), "qqq_gemm: all tensors must be on the device of A.");
+  TORCH_CHECK(s3.numel() == 0 || s3.get_device() == A.get_device(), "qqq_gemm: all tensors must be on the device of A.");
+  // the planner uses C (64*max_par rows of N int32) as split-K scratch up to that capacity: a smaller C would be overrun
+  TORCH_CHECK(prob_m == 0 || C.size(0) >= 64 * max_par, "C must have at least ", 64 * max_par, " rows.");
+  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && C.dim() == 2 && D.dim() == 2, "qqq_gemm: A, B, C, D must be matrices.");
+  TORCH_CHECK(B.size(0) * 16 == prob_k && B.size(1) == 2 * (int64_t)prob_n, "qqq_gemm: B must be [k/16, 2n] = [", prob_k / 16,
+              ", ", 2 * prob_n, "].");
+  TORCH_CHECK(D.size(0) == prob_m && D.size(1) == prob_n, "qqq_gemm: D must be [m, n] = [", prob_m, ", ", prob_n, "].");
+  TORCH_CHECK(s1.numel() == prob_m && s2.numel() == prob_n, "qqq_gemm: s1 needs m and s2 needs n elements.");
+  TORCH_CHECK(s3.numel() == 0 || s3.size(1) == prob_n, "qqq_gemm: s3 must be [k/groupsize, n].");
   const int dev = A.get_device();
   const int err = qqq_gemm_sm100a(A.data_ptr(), B.data_ptr(), C.data_ptr(), D.data_ptr(), s1.data_ptr(), s2.data_ptr(),
                                   s3.numel() ? s3.data_ptr() : nullptr, prob_m, prob_n, prob_k, workspace.data_ptr(),

@@ -9,7 +9,7 @@ nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc
 flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--compiler-options", "-fPIC"] + defs
 with tempfile.TemporaryDirectory() as td:
     objs, procs = [], []
-    for s in ("qqq_c_api.cu", "qqq_gemm_sm100.cu", "act_quant.cu"):
+    for s in ("qqq_c_api.cu", "qqq_gemm_sm100.cu", "act_quant.cu", "tp_reduce_quant.cu"):
         o = os.path.join(td, s + ".o")
         procs.append(subprocess.Popen([nvcc, "-c", os.path.join(CSRC, s), "-o", o] + flags))
         objs.append(o)

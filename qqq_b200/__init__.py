@@ -7,8 +7,8 @@ Public surface (mirrors the reference hot path only):
 """
 from .ops import dynamic_quant, launch_count, qqq_gemm  # noqa: F401
 from . import model  # noqa: F401
-from .qlinear import (QQQLinear, QuantLinear, merge_quant_linears, mul, pack_int4_weights,  # noqa: F401
+from .qlinear import (QQQLinear, QuantizedActivation, QuantLinear, merge_quant_linears, mul, pack_int4_weights,  # noqa: F401
                       set_act_quant_cache)
 
-__all__ = ["qqq_gemm", "dynamic_quant", "mul", "QuantLinear", "QQQLinear", "pack_int4_weights", "merge_quant_linears", "launch_count", "set_act_quant_cache"]
+__all__ = ["qqq_gemm", "dynamic_quant", "mul", "QuantLinear", "QQQLinear", "QuantizedActivation", "pack_int4_weights", "merge_quant_linears", "launch_count", "set_act_quant_cache"]
 __version__ = "0.1.0"

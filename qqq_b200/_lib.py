@@ -17,6 +17,8 @@ SYMBOLS = (
     "qqq_gemm_sm100a",
     "qqq_gemm_reduce_sm100a",
     "qqq_gemm_acc_sm100a",
+    "qqq_gemm_scatter_sm100a",
+    "qqq_tp_reduce_quant_sm100a",
     "qqq_act_quant_sm100a",
     "qqq_act_quant_strided_sm100a",
     "qqq_b200_version",
@@ -53,6 +55,10 @@ def load() -> ctypes.CDLL:
     lib.qqq_gemm_reduce_sm100a.restype = ci
     lib.qqq_gemm_acc_sm100a.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, ci]
     lib.qqq_gemm_acc_sm100a.restype = ci
+    lib.qqq_gemm_scatter_sm100a.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, ci]
+    lib.qqq_gemm_scatter_sm100a.restype = ci
+    lib.qqq_tp_reduce_quant_sm100a.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    lib.qqq_tp_reduce_quant_sm100a.restype = ci
     lib.qqq_act_quant_sm100a.argtypes = [vp, vp, vp, ci, ci, ci, vp]
     lib.qqq_act_quant_sm100a.restype = ci
     lib.qqq_act_quant_strided_sm100a.argtypes = [vp, ctypes.c_longlong, vp, vp, ci, ci, ci, vp]

@@ -13,8 +13,8 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libqqq_b200.so"
-SOURCES = ["qqq_c_api.cu", "qqq_gemm_sm100.cu", "act_quant.cu"]
-HEADERS = ["qqq_common.cuh", "qqq_gemm_sm100.h", "../../include/qqq_b200.h"]
+SOURCES = ["qqq_c_api.cu", "qqq_gemm_sm100.cu", "act_quant.cu", "tp_reduce_quant.cu"]
+HEADERS = ["qqq_common.cuh", "quant_common.cuh", "qqq_gemm_sm100.h", "../../include/qqq_b200.h"]
 
 
 def nvcc_path() -> str:

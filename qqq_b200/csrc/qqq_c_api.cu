@@ -365,9 +365,14 @@ int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_coun
   return QQQ_OK;
 }
 
+struct TpScatter {
+  int rank, world, rows;
+  void* const* part;
+};
+
 static int gemm_impl(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
                      int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
-                     int thread_k, int thread_n, int sms, int max_par, bool reduce, bool acc = false) {
+                     int thread_k, int thread_n, int sms, int max_par, int out_mode, const TpScatter* tp = nullptr) {
   using namespace qqq;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int M = prob_m, N = prob_n, K = prob_k;
@@ -432,11 +437,15 @@ static int gemm_impl(const void* A, const void* B, void* C, void* D, const void*
   int grid = 0;
   {
     const int rc = plan_gemm(M, N, K, grouped, sm_count, max_par, C != nullptr && workspace != nullptr, p, &grid,
-                             /*allow_pair=*/!reduce && !acc);
+                             /*allow_pair=*/out_mode == 0);
     if (rc != QQQ_OK) return rc;
   }
-  p.reduce = reduce ? 1 : 0;
-  p.acc = acc ? 1 : 0;
+  p.out_mode = out_mode;
+  if (tp != nullptr) {
+    p.tp_rank = tp->rank;
+    p.tp_rows = tp->rows;
+    for (int r = 0; r < 8; ++r) p.tp_part[r] = r < tp->world ? reinterpret_cast<__half*>(tp->part[r]) : nullptr;
+  }
   // weights are streamed once when a single token tile covers M; tokens are re-read by every CTA
   p.hint_b = p.m_tiles == 1 ? kEvictFirst : kEvictNormal;
   p.hint_a = kEvictLast;
@@ -464,20 +473,86 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
                     int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev, void* stream_,
                     int thread_k, int thread_n, int sms, int max_par) {
   return gemm_impl(A, B, C, D, s1, s2, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, thread_k, thread_n,
-                   sms, max_par, false);
+                   sms, max_par, 0);
 }
 
 int qqq_gemm_reduce_sm100a(const void* A, const void* B, void* C, void* D_multicast, const void* s1, const void* s2,
                            const void* s3, int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev,
                            void* stream_, int thread_k, int thread_n, int sms, int max_par) {
   return gemm_impl(A, B, C, D_multicast, s1, s2, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, thread_k,
-                   thread_n, sms, max_par, true);
+                   thread_n, sms, max_par, 1);
 }
 
 int qqq_gemm_acc_sm100a(const void* A, const void* B, void* C, void* D_int32, const void* s3, int prob_m, int prob_n,
                         int prob_k, void* workspace, int groupsize, int dev, void* stream_, int sms, int max_par) {
   return gemm_impl(A, B, C, D_int32, nullptr, nullptr, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, -1, -1,
-                   sms, max_par, false, true);
+                   sms, max_par, 2);
+}
+
+int qqq_gemm_scatter_sm100a(const void* A, const void* B, void* C, void* const* peer_partials, const void* s1, const void* s2,
+                            const void* s3, int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev,
+                            void* stream_, int sms, int max_par, int tp_rank, int tp_world, int tp_rows) {
+  if (peer_partials == nullptr || tp_world < 1 || tp_world > 8 || tp_rank < 0 || tp_rank >= tp_world || tp_rows < 1 ||
+      (long long)tp_rows * tp_world < prob_m) {
+    set_err("gemm_scatter: need 1 <= world <= 8, 0 <= rank < world, rows * world >= m (got rank=%d world=%d rows=%d m=%d)",
+            tp_rank, tp_world, tp_rows, prob_m);
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  for (int r = 0; r < tp_world; ++r)
+    if (peer_partials[r] == nullptr || (reinterpret_cast<uintptr_t>(peer_partials[r]) & 15)) {
+      set_err("gemm_scatter: partial-sum buffer of rank %d is null or not 16-byte aligned", r);
+      return QQQ_ERR_PROB_SHAPE;
+    }
+  const TpScatter tp{tp_rank, tp_world, tp_rows, peer_partials};
+  // D is unused; the alignment check of gemm_impl still wants a 16-byte aligned pointer
+  return gemm_impl(A, B, C, peer_partials[tp_rank], s1, s2, s3, prob_m, prob_n, prob_k, workspace, groupsize, dev, stream_, -1,
+                   -1, sms, max_par, 3, &tp);
+}
+
+int qqq_tp_reduce_quant_sm100a(const void* partials, void* const* a8_dst, void* a8_multicast, void* const* s1_dst,
+                               void* s1_multicast, void* h_out, const void* bias, void* flags, void* const* peer_flags,
+                               int tp_rank, int tp_world, int tp_rows, int prob_m, int prob_n, int dev, void* stream_) {
+  if (tp_world < 1 || tp_world > 8 || tp_rank < 0 || tp_rank >= tp_world || tp_rows < 1 ||
+      (long long)tp_rows * tp_world < prob_m || prob_m < 0 || prob_n <= 0 || prob_n % 8 != 0) {
+    set_err("tp_reduce_quant: bad geometry (rank=%d world=%d rows=%d m=%d n=%d)", tp_rank, tp_world, tp_rows, prob_m, prob_n);
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  if (partials == nullptr || flags == nullptr || peer_flags == nullptr || a8_dst == nullptr || s1_dst == nullptr ||
+      ((a8_multicast == nullptr) != (s1_multicast == nullptr))) {
+    set_err("tp_reduce_quant: null buffer (the two multicast addresses come together or not at all)");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  for (int r = 0; r < tp_world; ++r)
+    if (a8_dst[r] == nullptr || s1_dst[r] == nullptr || peer_flags[r] == nullptr ||
+        (reinterpret_cast<uintptr_t>(a8_dst[r]) & 15)) {
+      set_err("tp_reduce_quant: buffers of rank %d are null or misaligned", r);
+      return QQQ_ERR_PROB_SHAPE;
+    }
+  if ((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(h_out) | reinterpret_cast<uintptr_t>(bias) |
+       reinterpret_cast<uintptr_t>(a8_multicast)) & 15) {
+    set_err("tp_reduce_quant: partials, h_out, bias and the multicast address must be 16-byte aligned");
+    return QQQ_ERR_PROB_SHAPE;
+  }
+  const DeviceInfo* di = device_info(dev);
+  if (!di) {
+    set_err("cannot query device %d", dev);
+    return QQQ_ERR_CUDA;
+  }
+  if (di->cc_major != 10) {
+    set_err("device %d has compute capability %d.x; this library is sm_100a only", dev, di->cc_major);
+    return QQQ_ERR_DEVICE;
+  }
+  DeviceGuard guard(dev);
+  if (!guard.ok) return QQQ_ERR_CUDA;
+  cudaError_t e = qqq::launch_tp_reduce_quant(partials, a8_dst, a8_multicast, s1_dst, s1_multicast, h_out, bias, flags,
+                                              peer_flags, tp_rank, tp_world, tp_rows, prob_m, prob_n,
+                                              reinterpret_cast<cudaStream_t>(stream_), use_pdl());
+  if (e != cudaSuccess) {
+    set_err("tp_reduce_quant launch failed: %s", cudaGetErrorString(e));
+    return QQQ_ERR_CUDA;
+  }
+  g_launches.fetch_add(1);
+  return QQQ_OK;
 }
 
 int qqq_act_quant_strided_sm100a(const void* x, long long ldx, void* q, void* s1, int prob_m, int prob_k, int dev,

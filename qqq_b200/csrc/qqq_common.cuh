@@ -252,4 +252,8 @@ constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 cudaError_t launch_act_quant(const void* x, long long ldx, void* q, void* s1, int M, int K, cudaStream_t stream,
                              bool pdl);
 
+cudaError_t launch_tp_reduce_quant(const void* part, void* const* a8_dst, void* a8_mc, void* const* s1_dst, void* s1_mc,
+                                   void* h_out, const void* bias, void* flags, void* const* peer_flags, int rank, int world,
+                                   int rows_cap, int M, int N, cudaStream_t stream, bool pdl);
+
 }  // namespace qqq

@@ -139,14 +139,30 @@ __device__ __forceinline__ uint32_t unpack_pg4(uint32_t w, uint32_t s2h) {
   return out;
 }
 
-// How a finished 16-byte piece of an output row leaves the SM.  kReduce = false: a plain store into D.
-// kReduce = true (tensor-parallel row shards, qqq_gemm_reduce_sm100a): D is a MULTICAST address bound to the same
-// buffer on every rank; `multimem.red` adds the eight fp16 values into every replica (the NVSwitch fans the
-// reduction out), so once all ranks' kernels have finished every replica holds the all-reduced output — the
-// collective rides in the epilogue instead of following the GEMM as a separate NCCL call.
-template <bool kReduce>
+// How a finished 16-byte piece (8 channels of token row m) of the output leaves the SM.
+//   kOutStore  : a plain store into D.
+//   kOutReduce : (tensor-parallel row shards, qqq_gemm_reduce_sm100a) D is a MULTICAST address bound to the same buffer on
+//                every rank; `multimem.red` adds the eight fp16 values into every replica (the NVSwitch fans the reduction
+//                out), so once all ranks' kernels have finished every replica holds the all-reduced output — one-shot
+//                all-reduce in the epilogue.
+//   kOutScatter: (qqq_gemm_scatter_sm100a) the row goes to the rank that OWNS it (owner = m / tp_rows), into the slot of this
+//                rank in the owner's partial-sum buffer [world][tp_rows][N] — a peer store over NVLink, issued tile by tile
+//                while the GEMM runs: the reduce-scatter half of the exchange; tp_reduce_quant.cu is the other half.
+//   kOutAcc    : raw int32 accumulators (handled in the epilogue loop, not here).
+enum : int { kOutStore = 0, kOutReduce = 1, kOutAcc = 2, kOutScatter = 3 };
+
+template <int kOut>
+__device__ __forceinline__ __half* out_row(const GemmParams& p, int m) {
+  if constexpr (kOut == kOutScatter) {
+    const int owner = m / p.tp_rows;
+    return p.tp_part[owner] + (size_t)(p.tp_rank * p.tp_rows + (m - owner * p.tp_rows)) * p.N;
+  } else {
+    return p.D + (size_t)m * p.N;
+  }
+}
+template <int kOut>
 __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
-  if constexpr (kReduce) {
+  if constexpr (kOut == kOutReduce) {
     asm volatile("multimem.red.relaxed.sys.global.add.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(dp), "r"(v.x), "r"(v.y),
                  "r"(v.z), "r"(v.w)
                  : "memory");
@@ -169,7 +185,7 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
 //
 // One 16-token chunk of this lane's channel, whole-tile case: TMEM -> fp32 * s2 * s1 -> fp16 -> warp-private smem tile
 // -> 16-byte row stores (same arithmetic and order as the epilogue warps' `process`).
-template <bool kReduce>
+template <int kOut>
 __device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t (&r)[16], int m0, int mb, int rows,
                                                    int col0 /* nt*128 + 32q */, bool q_ok, float s2v, unsigned short* stg,
                                                    int lane, const int* __restrict__ partials, int others,
@@ -192,9 +208,8 @@ __device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t
     const int st_tok = lane >> 2, st_part = lane & 3;
     const uint4* rp = reinterpret_cast<const uint4*>(stg) + lane;
     const uint4 v0 = rp[0], v1 = rp[32];
-    __half* dp = p.D + (size_t)(m0 + mb + st_tok) * p.N + (col0 + 8 * st_part);
-    if (mb + st_tok < rows) emit_d<kReduce>(dp, v0);
-    if (mb + st_tok + 8 < rows) emit_d<kReduce>(dp + (size_t)8 * p.N, v1);
+    if (mb + st_tok < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok) + (col0 + 8 * st_part), v0);
+    if (mb + st_tok + 8 < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok + 8) + (col0 + 8 * st_part), v1);
   }
   __syncwarp();
 }
@@ -202,10 +217,11 @@ __device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t
 
 // kAcc (qqq_gemm_acc_sm100a): the finished tile leaves as the raw int32 accumulators, row-major [M, N] int32, no scales —
 // for the bit-exact tensor-parallel mode (int32 partial sums are all-reduced, the scales applied once afterwards).
-template <bool GROUPED, bool kPair, bool kReduce = false, bool kAcc = false>
+template <bool GROUPED, bool kPair, int kOut = kOutStore>
 __global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
+  constexpr bool kAcc = kOut == kOutAcc;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -506,12 +522,12 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           tmem_wait_ld();
           const int mb2 = mb + 64;
           if (mb2 < rows) tmem_ld_32x32b_x16(tmem_d + mb2, rb);
-          helper_drain_chunk<kReduce>(p, ra, m0, mb, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
+          helper_drain_chunk<kOut>(p, ra, m0, mb, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
           if (mb2 >= rows) break;
           tmem_wait_ld();
           mb = mb2 + 64;
           if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
-          helper_drain_chunk<kReduce>(p, rb, m0, mb2, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
+          helper_drain_chunk<kOut>(p, rb, m0, mb2, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
         }
       }
       tc_fence_before();
@@ -754,9 +770,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (q_ok) {  // the whole 32-channel quadrant is inside N (N % 64 == 0) or outside
             const uint4* rp = reinterpret_cast<const uint4*>(stg) + lane;  // row st_tok, part st_part
             const uint4 v0 = rp[0], v1 = rp[32];                            // rows st_tok and st_tok + 8
-            __half* dp = p.D + (size_t)(m0 + mb + st_tok) * p.N + (nt * kTileN + 32 * q + 8 * st_part);
-            if (mb + st_tok < rows) emit_d<kReduce>(dp, v0);
-            if (mb + st_tok + 8 < rows) emit_d<kReduce>(dp + (size_t)8 * p.N, v1);
+            const int col = nt * kTileN + 32 * q + 8 * st_part;
+            if (mb + st_tok < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok) + col, v0);
+            if (mb + st_tok + 8 < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok + 8) + col, v1);
           }
           __syncwarp();  // the tile is rewritten by the next chunk
         } else {
@@ -835,19 +851,21 @@ size_t gemm_smem_bytes(const GemmParams& p) {
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
-  static bool attr_set[8][64] = {};  // the opt-in shared-memory attribute is per device
+  static bool attr_set[10][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
-  if ((p.reduce || p.acc) && p.pair) return cudaErrorInvalidValue;  // the planner never pairs these launches
-  if (p.reduce && p.acc) return cudaErrorInvalidValue;
-  const int variant = p.acc ? 6 + (grouped ? 1 : 0) : p.reduce ? 4 + (grouped ? 1 : 0) : (grouped ? 1 : 0) + (p.pair ? 2 : 0);
+  if (p.out_mode != kOutStore && p.pair) return cudaErrorInvalidValue;  // the planner never pairs these launches
+  if (p.out_mode < 0 || p.out_mode > kOutScatter) return cudaErrorInvalidValue;
+  const int variant = p.out_mode != kOutStore ? 2 + 2 * p.out_mode + (grouped ? 1 : 0) : (grouped ? 1 : 0) + (p.pair ? 2 : 0);
   auto kern = variant == 0 ? qqq_gemm_kernel<false, false>
             : variant == 1 ? qqq_gemm_kernel<true, false>
             : variant == 2 ? qqq_gemm_kernel<false, true>
             : variant == 3 ? qqq_gemm_kernel<true, true>
-            : variant == 4 ? qqq_gemm_kernel<false, false, true>
-            : variant == 5 ? qqq_gemm_kernel<true, false, true>
-            : variant == 6 ? qqq_gemm_kernel<false, false, false, true>
-                           : qqq_gemm_kernel<true, false, false, true>;
+            : variant == 4 ? qqq_gemm_kernel<false, false, kOutReduce>
+            : variant == 5 ? qqq_gemm_kernel<true, false, kOutReduce>
+            : variant == 6 ? qqq_gemm_kernel<false, false, kOutAcc>
+            : variant == 7 ? qqq_gemm_kernel<true, false, kOutAcc>
+            : variant == 8 ? qqq_gemm_kernel<false, false, kOutScatter>
+                           : qqq_gemm_kernel<true, false, kOutScatter>;
   if (dev < 0 || dev >= 64 || !attr_set[variant][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) return e;

@@ -62,8 +62,12 @@ struct GemmParams {
   int b_tiles;  // tiles [a_tiles, a_tiles + b_tiles) are processed whole: CTA b owns b_tpc consecutive ones
   int b_tpc;
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
-  int reduce;               // 1: D is a multicast address and the epilogue adds into it (multimem.red) instead of storing
-  int acc;                  // 1: D is int32 [M, N] and receives the raw accumulators (no scales)
+  int out_mode;             // 0: store D;  1: D is a multicast address and the epilogue adds into it (multimem.red);
+                            // 2: D is int32 [M, N] and receives the raw accumulators (no scales);  3: scatter (below)
+  // out_mode 3 (tensor-parallel row shards): token row m goes to rank m / tp_rows, into slot tp_rank of that rank's
+  // partial-sum buffer tp_part[owner] = fp16 [world][tp_rows][N] (peer-mapped pointers)
+  int tp_rank, tp_rows;
+  __half* tp_part[8];
 };
 
 size_t gemm_smem_bytes(const GemmParams& p);

@@ -158,7 +158,9 @@ def pack_model(model: nn.Module, quantizers, bits: int, group_size: int, pack_de
     qlayers = find_layers(model, [QuantLinear])
     for name in quantizers:
         scale, zero, g_idx, s_extra = quantizers[name]
-        ql, lin = qlayers[name], layers[name]
+        # the source Linear is released as soon as it is packed (reference: `del layers[name]; free_memory()`,
+        # apply_gptq.py:86-87): peak memory is the packed model plus ONE fp16 layer, not plus the whole fp16 model
+        ql, lin = qlayers[name], layers.pop(name)
         dev = ql.B.device
         if pack_device is not None:
             ql.to(pack_device)
@@ -166,6 +168,9 @@ def pack_model(model: nn.Module, quantizers, bits: int, group_size: int, pack_de
         pdev = ql.B.device
         ql.pack(lin, scale.to(pdev), s_extra.to(pdev) if s_extra is not None else None)
         ql.to(dev)
+        del lin
+        if dev.type == "cuda" or (pack_device is not None and torch.device(pack_device).type == "cuda"):
+            torch.cuda.empty_cache()
     return model
 
 
@@ -247,19 +252,30 @@ class _SharedGemm(nn.Module):
         super().__init__()
         self.merged = merged
         self._key = None
+        self._ref = None  # keeps the keyed input alive: its address cannot be handed to another tensor while we hold it
         self._out = None
         self._served = 0
 
+    @staticmethod
+    def _key_of(x: torch.Tensor):
+        # inference tensors have no version counter (reading `_version` raises); for them identity of the tensor object,
+        # which `_ref` keeps alive, stands in for it
+        ver = id(x) if x.is_inference() else x._version
+        return (x.untyped_storage().data_ptr(), x.storage_offset(), tuple(x.shape), tuple(x.stride()), x.dtype, ver, x.device)
+
     def slice(self, x: torch.Tensor, index: int) -> torch.Tensor:
-        key = (x.data_ptr(), x._version, tuple(x.shape), x.device)
-        if self._key != key or self._out is None:
+        key = self._key_of(x)
+        # slot 0 (q_proj / gate_proj) is always called first in a forward: it always recomputes, so an entry left behind by an
+        # interrupted forward (an exception between q_proj and v_proj) can never be served to the next one
+        if index == 0 or self._key != key or self._out is None:
+            self._key, self._ref, self._out = None, None, None
             self._out = self.merged(x).split(self.merged.split_sizes, dim=-1)
-            self._key = key
+            self._key, self._ref = key, x
             self._served = 0
         y = self._out[index]
         self._served += 1
-        if self._served == len(self.merged.split_sizes):  # every consumer has its slice: drop the reference
-            self._key, self._out = None, None
+        if self._served == len(self.merged.split_sizes):  # every consumer has its slice: drop the references
+            self._key, self._ref, self._out = None, None, None
         return y
 
 

@@ -121,6 +121,48 @@ def qqq_gemm_reduce(A, B, C, d_multicast_ptr: int, s1, s2, s3, workspace, prob_n
         raise RuntimeError(f"qqq_gemm_reduce_sm100a failed (rc={err}): {_lib.last_error()}")
 
 
+def _ptr_array(ptrs):
+    import ctypes
+
+    return (ctypes.c_void_p * len(ptrs))(*[int(v) for v in ptrs])
+
+
+def qqq_gemm_scatter(A, B, C, peer_partials, s1, s2, s3, workspace, prob_n: int, tp_rank: int, tp_world: int, tp_rows: int,
+                     max_par=16, sms=-1):
+    """Row-shard GEMM whose epilogue stores output row m into slot `tp_rank` of the partial-sum buffer of the rank that owns
+    the row (m // tp_rows): qqq_gemm_scatter_sm100a in include/qqq_b200.h.  `peer_partials`: tp_world device addresses
+    (peer-mapped) of the fp16 [tp_world][tp_rows][prob_n] buffers.  Followed on every rank by `tp_reduce_quant`."""
+    prob_m, prob_k = A.size(0), A.size(1)
+    groupsize = -1 if s3.numel() == 0 else prob_k // s3.size(0)
+    if not A.is_cuda:
+        raise RuntimeError("qqq_gemm_scatter: tensors must be CUDA tensors (qqq_b200 has no CPU path).")
+    if len(peer_partials) != tp_world:
+        raise RuntimeError("qqq_gemm_scatter: one partial-sum buffer address per rank is required.")
+    if workspace.numel() < prob_n // 128 * max_par or C.numel() < 64 * max_par * prob_n:
+        raise RuntimeError("qqq_gemm_scatter: workspace / C too small.")
+    dev = A.get_device()
+    err = _lib.load().qqq_gemm_scatter_sm100a(
+        _ptr(A), _ptr(B), _ptr(C), _ptr_array(peer_partials), _ptr(s1), _ptr(s2), _ptr(s3) if s3.numel() else None,
+        prob_m, prob_n, prob_k, _ptr(workspace), groupsize, dev, torch.cuda.current_stream(dev).cuda_stream, sms, max_par,
+        tp_rank, tp_world, tp_rows,
+    )
+    if err != 0:
+        raise RuntimeError(f"qqq_gemm_scatter_sm100a failed (rc={err}): {_lib.last_error()}")
+
+
+def tp_reduce_quant(partials_ptr: int, a8_dst, a8_mc: int, s1_dst, s1_mc: int, h_out, bias, flags_ptr: int, peer_flags,
+                    tp_rank: int, tp_world: int, tp_rows: int, prob_m: int, prob_n: int, dev: int):
+    """Second half of the fused row-parallel exchange (qqq_tp_reduce_quant_sm100a): sum the partial-sum slots of this rank's
+    rows, quantise per token, deliver int8 rows + scales to every rank.  Addresses are plain ints (symmetric memory)."""
+    err = _lib.load().qqq_tp_reduce_quant_sm100a(
+        partials_ptr, _ptr_array(a8_dst), a8_mc or None, _ptr_array(s1_dst), s1_mc or None,
+        _ptr(h_out) if h_out is not None else None, _ptr(bias) if bias is not None else None, flags_ptr,
+        _ptr_array(peer_flags), tp_rank, tp_world, tp_rows, prob_m, prob_n, dev, torch.cuda.current_stream(dev).cuda_stream,
+    )
+    if err != 0:
+        raise RuntimeError(f"qqq_tp_reduce_quant_sm100a failed (rc={err}): {_lib.last_error()}")
+
+
 def dynamic_quant(x: torch.Tensor):
     """Per-token int8 quantisation, bit-identical to the reference's 5 eager ops
     (qlinear_marlin.py:265-268), as ONE kernel.  x fp16 [M,K] -> (int8 [M,K], fp32 [M,1])."""

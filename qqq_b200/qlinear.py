@@ -14,6 +14,7 @@ What differs underneath:
 from __future__ import annotations
 
 from logging import getLogger
+from typing import NamedTuple
 
 import torch
 import torch.nn as nn
@@ -71,6 +72,16 @@ def pack_int4_weights(w: torch.Tensor, per_group: bool) -> torch.Tensor:
     return word.to(torch.int32)
 
 
+class QuantizedActivation(NamedTuple):
+    """An activation that already went through `dynamic_quant` (reference: qlinear_marlin.py:265-268): what the fused
+    tensor-parallel exchange (tp.ScatterRowParallelQuantLinear) hands to the linears of the next block, and what linears
+    that share an input can share.  `QuantLinear.forward` accepts it in place of the fp16 tensor."""
+
+    q: torch.Tensor   # int8 [M, K]
+    s1: torch.Tensor  # fp32 [M, 1]
+    lead: tuple = ()  # leading dims of the original activation (output is reshaped to lead + (N,)); () -> (M,)
+
+
 class _ActQuantCache:
     """Last (input -> int8, scale) pair of `dynamic_quant`, so that linears that consume the SAME tensor (q/k/v,
     gate/up in the reference's 7-module layer structure) quantise it once.  Opt-in (`set_act_quant_cache(True)`):
@@ -85,16 +96,25 @@ class _ActQuantCache:
 
     @classmethod
     def key(cls, x):
+        # inference tensors (torch.inference_mode) have no version counter — reading `_version` raises — and may still be
+        # written in place inside inference mode: they are never cached (every linear quantises for itself, as the reference)
+        if x.is_inference():
+            return None
         return (x.untyped_storage().data_ptr(), x.storage_offset(), tuple(x.shape), tuple(x.stride()), x.dtype, x._version,
                 x.device)
 
     @classmethod
     def get(cls, x):
-        return cls._val if cls._key is not None and cls._key == cls.key(x) else None
+        k = cls.key(x)
+        return cls._val if k is not None and cls._key == k else None
 
     @classmethod
     def put(cls, x, val):
-        cls._key, cls._ref, cls._val = cls.key(x), x, val
+        k = cls.key(x)
+        if k is None:
+            cls.clear()
+        else:
+            cls._key, cls._ref, cls._val = k, x, val
 
     @classmethod
     def clear(cls):
@@ -220,16 +240,20 @@ class QuantLinear(nn.Module):
         return ops.dynamic_quant(x)
 
     def forward(self, A):
-        out_shape = A.shape[:-1] + (self.outfeatures,)
-        A = A.reshape(-1, A.shape[-1]).half()
-        cached = _ActQuantCache.get(A) if _ActQuantCache.enabled else None
-        if cached is not None:
-            quant_A, s1 = cached
+        if isinstance(A, QuantizedActivation):
+            quant_A, s1 = A.q, A.s1
+            out_shape = (tuple(A.lead) if A.lead else (quant_A.shape[0],)) + (self.outfeatures,)
         else:
-            quant_A, s1 = self.dynamic_quant(A)
-            if _ActQuantCache.enabled:
-                _ActQuantCache.put(A, (quant_A, s1))
-        D = torch.empty(A.shape[0], self.outfeatures, dtype=A.dtype, device=A.device)
+            out_shape = A.shape[:-1] + (self.outfeatures,)
+            A = A.reshape(-1, A.shape[-1]).half()
+            cached = _ActQuantCache.get(A) if _ActQuantCache.enabled else None
+            if cached is not None:
+                quant_A, s1 = cached
+            else:
+                quant_A, s1 = self.dynamic_quant(A)
+                if _ActQuantCache.enabled:
+                    _ActQuantCache.put(A, (quant_A, s1))
+        D = torch.empty(quant_A.shape[0], self.outfeatures, dtype=torch.float16, device=quant_A.device)
         mul(quant_A, self.B, self.reduce_buffer, D, s1, self.s_channel, self.s_group, self.workspace,
             max_par=self.max_par)
         D = D.reshape(out_shape)
@@ -268,4 +292,4 @@ def merge_quant_linears(mods) -> QuantLinear:
 
 QQQLinear = QuantLinear
 
-__all__ = ["QuantLinear", "QQQLinear", "mul", "pack_int4_weights", "merge_quant_linears", "set_act_quant_cache"]
+__all__ = ["QuantLinear", "QQQLinear", "QuantizedActivation", "mul", "pack_int4_weights", "merge_quant_linears", "set_act_quant_cache"]

@@ -15,7 +15,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import ops
-from .qlinear import QuantLinear
+from .qlinear import QuantizedActivation, QuantLinear
 
 
 def split_sizes(total: int, world: int, unit: int):
@@ -79,13 +79,26 @@ class ColumnParallelQuantLinear(nn.Module):
         self.group = group
 
     def forward(self, x):
+        """x: the replicated fp16 activation, or the `QuantizedActivation` a ScatterRowParallelQuantLinear delivered."""
         y = self.shard(x)
         if not self.gather_output:
             return y
         world = dist.get_world_size(self.group)
-        parts = [torch.empty_like(y) for _ in range(world)]  # equal shards only
-        dist.all_gather(parts, y.contiguous(), group=self.group)
-        return torch.cat(parts, dim=-1)
+        rank = dist.get_rank(self.group)
+        # shards may be uneven (split_sizes: N/64 blocks do not always divide by world): every rank's width is known
+        # from the split rule, so uneven gathers need no size exchange
+        widths = torch.tensor([y.shape[-1]], device=y.device)
+        all_w = [torch.empty_like(widths) for _ in range(world)]
+        dist.all_gather(all_w, widths, group=self.group)
+        all_w = [int(w.item()) for w in all_w]
+        wmax = max(all_w)
+        y2 = y.reshape(-1, y.shape[-1])
+        if all_w[rank] < wmax:
+            y2 = torch.nn.functional.pad(y2, (0, wmax - all_w[rank]))
+        parts = [torch.empty_like(y2) for _ in range(world)]
+        dist.all_gather(parts, y2.contiguous(), group=self.group)
+        out = torch.cat([t[:, :w] for t, w in zip(parts, all_w)], dim=-1)
+        return out.reshape(y.shape[:-1] + (out.shape[-1],))
 
 
 class RowParallelQuantLinear(nn.Module):
@@ -253,3 +266,143 @@ class FusedRowParallelQuantLinear(nn.Module):
         self.ws.end()
         out = out.reshape(out_shape)
         return out + self.bias if self.bias is not None else out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row-parallel exchange fused into the kernels on both sides of it: reduce-scatter in the GEMM epilogue (peer stores),
+# all-gather in the activation quantisation of the next block (multicast stores).  No collective-library call.
+# ---------------------------------------------------------------------------------------------------------------
+class _SymmBytesBackend:
+    """torch symmetric memory as plumbing: ONE byte buffer per rank, peer-mapped on every rank (+ its NVLS multicast
+    address when the fabric has one)."""
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.symm = symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self._hdls = []  # keep every mapping alive as long as the backend lives
+
+    def alloc(self, nbytes: int, device):
+        """-> (local uint8 tensor (zeroed, all ranks synchronised), [address on rank r for r in ranks], multicast address | 0)"""
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        t = self.symm.empty(nbytes, dtype=torch.uint8, device=device)
+        hdl = self.symm.rendezvous(t, self.group)
+        t.zero_()
+        torch.cuda.synchronize(device)
+        hdl.barrier(channel=0)
+        torch.cuda.synchronize(device)
+        self._hdls.append(hdl)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        return t, [int(a) for a in hdl.buffer_ptrs], mc
+
+
+class ScatterWorkspace:
+    """Symmetric buffers shared by every ScatterRowParallelQuantLinear of a model (they run one after the other):
+
+        partial  fp16 [world][rows][N]   slot s: rank s's partial output for the rows THIS rank owns (written by peers)
+        a8       int8 [world*rows][N]    the gathered quantised activations, identical on every rank after a call
+        s1       fp32 [world*rows]       their per-token scales
+        flags    uint32 [32]             epoch flags of the in-kernel cross-rank synchronisation (see tp_reduce_quant.cu)
+
+    with rows = ceil(M / world) chosen per call.  One buffer set is enough: a rank can only overwrite `partial` / `a8` of a
+    peer after that peer has finished reading them (arrive-1 / arrive-2 flags), see the kernel's header."""
+
+    def __init__(self, max_tokens: int, max_features: int, group=None, device=None, backend=None, use_multicast=True):
+        self.backend = backend if backend is not None else _SymmBytesBackend(group)
+        self.rank, self.world = self.backend.rank, self.backend.world
+        self.max_tokens, self.max_features = max_tokens, max_features
+        rows = -(-max_tokens // self.world)
+        mpad = rows * self.world
+        al = lambda n: (n + 255) // 256 * 256  # noqa: E731
+        self.off_part = 0
+        self.off_a8 = self.off_part + al(2 * mpad * max_features)
+        self.off_s1 = self.off_a8 + al(mpad * max_features)
+        self.off_flags = self.off_s1 + al(4 * mpad)
+        nbytes = self.off_flags + 256
+        self.buf, self.ptrs, mc = self.backend.alloc(nbytes, device)
+        self.mc = mc if use_multicast else 0
+        self.calls = 0
+
+    def geometry(self, M: int, N: int):
+        if M > self.max_tokens or N > self.max_features:
+            raise RuntimeError(f"ScatterWorkspace: {M} x {N} exceeds the capacity {self.max_tokens} x {self.max_features}")
+        return -(-M // self.world)  # rows owned per rank
+
+    def views(self, M: int, N: int):
+        """This rank's (a8 [M, N] int8, s1 [M, 1] fp32) views of the gathered buffers."""
+        a8 = self.buf[self.off_a8:self.off_a8 + M * N].view(torch.int8).view(M, N)
+        s1 = self.buf[self.off_s1:self.off_s1 + 4 * M].view(torch.float32).view(M, 1)
+        return a8, s1
+
+    def timeouts(self) -> int:
+        """Number of in-kernel waits that gave up (2 s) since the workspace was created: 0 unless a rank went missing."""
+        return int(self.buf[self.off_flags:self.off_flags + 128].view(torch.int32)[18].item())
+
+
+class ScatterRowParallelQuantLinear(nn.Module):
+    """Row-parallel linear (o_proj / down_proj; split K) whose exchange is fused into the kernels around it:
+
+        x_local --act-quant--> GEMM on this rank's K-shard; epilogue stores each output row into the partial-sum slot of
+                               the rank that owns the row (peer stores over NVLink, qqq_gemm_scatter_sm100a)
+                --------------> owner: fp32 sum of the `world` fp16 partials in rank order -> fp16 (+ bias) -> per-token
+                               int8 quantisation -> int8 rows + scales multicast to every rank (qqq_tp_reduce_quant_sm100a)
+
+    Returns the `QuantizedActivation` of the all-reduced output for ALL tokens (what the next block's column-parallel
+    linears consume: pass it to ColumnParallelQuantLinear / QuantLinear.forward); with keep_hidden=True `self.hidden`
+    holds this rank's rows of the fp16 sum (sequence-sharded residual stream).  Numerics: per-shard activation scales
+    like RowParallelQuantLinear; the cross-rank sum is fp32 in rank order, rounded once — deterministic, reproduced bit
+    for bit by `reference_reduce_quant` below."""
+
+    def __init__(self, shard: QuantLinear, workspace: ScatterWorkspace, keep_hidden: bool = False):
+        super().__init__()
+        self.shard = shard
+        object.__setattr__(self, "ws", workspace)
+        self.keep_hidden = keep_hidden
+        self.hidden = None
+        self.bias = _replicated_bias(shard, getattr(workspace.backend, "group", None))
+
+    def forward(self, x_local):
+        ql, ws = self.shard, self.ws
+        if isinstance(x_local, QuantizedActivation):
+            q, s1, lead = x_local.q, x_local.s1, x_local.lead
+        else:
+            lead = tuple(x_local.shape[:-1])
+            q, s1 = ql.dynamic_quant(x_local.reshape(-1, x_local.shape[-1]).half())
+        M, N = q.shape[0], ql.outfeatures
+        rows = ws.geometry(M, N)
+        base = ws.ptrs
+        ops.qqq_gemm_scatter(q, ql.B, ql.reduce_buffer, [b + ws.off_part for b in base], s1, ql.s_channel, ql.s_group,
+                             ql.workspace, N, ws.rank, ws.world, rows, ql.max_par)
+        h = None
+        if self.keep_hidden:
+            my_rows = max(0, min(rows, M - ws.rank * rows))
+            h = torch.empty(max(my_rows, 1), N, dtype=torch.float16, device=q.device)
+        dev = q.get_device() if q.is_cuda else -1
+        ops.tp_reduce_quant(base[ws.rank] + ws.off_part, [b + ws.off_a8 for b in base], ws.mc + ws.off_a8 if ws.mc else 0,
+                            [b + ws.off_s1 for b in base], ws.mc + ws.off_s1 if ws.mc else 0, h, self.bias,
+                            base[ws.rank] + ws.off_flags, [b + ws.off_flags for b in base], ws.rank, ws.world, rows, M, N, dev)
+        ws.calls += 1
+        if self.keep_hidden:
+            self.hidden = h[:max(0, min(rows, M - ws.rank * rows))]
+        a8, s1g = ws.views(M, N)
+        return QuantizedActivation(a8, s1g, lead)
+
+
+def reference_reduce_quant(partials, bias=None):
+    """Torch restatement of qqq_tp_reduce_quant_sm100a for tests / the bench's parity leg: `partials` = the fp16 [M, N]
+    partial outputs of ranks 0..world-1 -> (h fp16 [M, N], a8 int8 [M, N], s1 fp32 [M, 1]).  Same operation order: fp32
+    adds in rank order starting from 0, one rounding to fp16, fp16 bias add, then the reference's quantisation expression
+    (qlinear_marlin.py:265-268) as it evaluates on a CUDA device."""
+    acc = torch.zeros_like(partials[0], dtype=torch.float32)
+    for p in partials:
+        acc = acc + p.float()
+    h = acc.half()
+    if bias is not None:
+        h = h + bias
+    s1 = h.abs().max(dim=-1, keepdim=True)[0].div(127.0).to(torch.float32)
+    a8 = (h / s1).round().clamp(-128, 127).to(torch.int8)
+    return h, a8, s1

@@ -41,9 +41,10 @@ def test_contract_keys(line):
 
 
 def test_launch_accounting_matches_the_call_structure(line):
-    # 2 tiny layers x 7 linears x (activation quant + GEMM); the cache variant quantises shared inputs once
-    assert line["gpu_launches_per_step"] == 28 and line["gpu_launches"] == 28 * line["steps"]
-    assert line["shared_act_quant"]["gpu_launches_per_step"] == 14 + 8
+    # 2 tiny layers x (7 GEMMs + 4 activation quants: q/k/v and gate/up share theirs); the reference's literal structure
+    # (every linear quantises for itself) is the `per_module_quant` section
+    assert line["gpu_launches_per_step"] == 14 + 8 and line["gpu_launches"] == 22 * line["steps"]
+    assert line["per_module_quant"]["gpu_launches_per_step"] == 28
 
 
 def test_auxiliary_sections_present(line):
@@ -63,7 +64,7 @@ def test_a_failing_auxiliary_section_does_not_cost_the_line():
 
 def test_flags_skip_sections():
     line = _run("--no-sweep", "--no-cpu", "--no-merged", "--no-decode", "--no-full")
-    for k in ("gemm_sweep", "gemm_sweep_transposed", "cpu_baseline", "decode_g128", "shared_act_quant", "full_forward"):
+    for k in ("gemm_sweep", "gemm_sweep_transposed", "cpu_baseline", "decode_g128", "per_module_quant", "full_forward"):
         assert k not in line
     assert line["merged"] is None
 
@@ -81,9 +82,23 @@ def test_two_ranks_tensor_parallel_prints_one_line_from_rank0():
     lines = _torchrun(HELPER, "--gpus", "2")
     assert len(lines) == 1
     line = lines[0]
-    assert line["n_gpus"] == 2 and line["config"]["parallelism"] == "tp2" and line["scaling"] == "strong"
-    assert line["gpu_launches_per_step"] == 28  # per rank: every linear still runs, on its shard
+    assert line["n_gpus"] == 2 and line["config"]["parallelism"].startswith("tp2") and line["scaling"] == "strong"
+    # default exchange: fused into the kernels (scatter GEMM + reduce/quant/gather), emulated over gloo here
+    assert line["tp_mode"] == "scatter" and line["tp_parity"]["green"] is True and line["exchange_timeouts"] == 0
+    # per rank and layer: 7 GEMMs + 2 local activation quants (inputs of o / down) + 2 reduce-quant kernels; + 1 quant of x
+    assert line["gpu_launches_per_step"] == 2 * 11 + 1
+    assert line["e2e"]["d2h_bytes_per_step"] * 2 == line["e2e"]["h2d_bytes_per_step"]  # this rank's half of the rows
     assert "gemm_sweep" not in line and "cpu_baseline" not in line  # rank 0 at N = 1 only
+    rows = line["gemm_sweep_tp"]
+    assert {r["split"] for r in rows} == {"N", "K"} and {r["mode"] for r in rows} == {"per-channel", "g128"}
+    assert all("fused_exchange_us" in r and "nccl_allreduce_us" in r for r in rows if r["split"] == "K")
+    assert line["llama2_70b_tp"]["value"] > 0 and line["llama2_70b_tp"]["exchange_timeouts"] == 0
+
+
+def test_two_ranks_nccl_mode():
+    lines = _torchrun(HELPER, "--gpus", "2", "--tp-mode", "nccl", "--no-70b", "--no-tp-sweep", port=29549)
+    assert len(lines) == 1 and lines[0]["tp_mode"] == "nccl" and lines[0]["tp_parity"]["green"] is True
+    assert lines[0]["gpu_launches_per_step"] == 22 and lines[0]["merged"]["value"] > 0
 
 
 def test_reference_arm_under_torchrun_only_rank0_speaks():
@@ -96,7 +111,7 @@ def test_reference_arm_under_torchrun_only_rank0_speaks():
 def test_two_ranks_with_the_all_reduce_fused_into_the_gemm():
     """--fused-allreduce wiring (row-parallel linears reduce in their own epilogue; multicast emulated over gloo): same
     launch count, no NCCL all-reduce in the chain, and the same numbers as the unfused run up to fp16 summation order."""
-    fused = _torchrun(HELPER, "--gpus", "2", "--fused-allreduce", port=29547)
+    fused = _torchrun(HELPER, "--gpus", "2", "--fused-allreduce", "--no-70b", "--no-tp-sweep", port=29547)
     assert len(fused) == 1
-    assert "fused into the GEMM epilogue" in fused[0]["config"]["parallelism"]
-    assert fused[0]["gpu_launches_per_step"] == 28 and fused[0]["merged"]["value"] > 0
+    assert "multimem.red" in fused[0]["config"]["parallelism"] and fused[0]["tp_mode"] == "reduce"
+    assert fused[0]["gpu_launches_per_step"] == 22

@@ -261,3 +261,175 @@ def test_exact_row_parallel_is_bit_equal_to_one_gpu_gloo(gs):
         pr.join(timeout=60)
         assert pr.exitcode == 0
     assert ok, "exact row-parallel mode must reproduce the 1-GPU output bit for bit on every rank (bias included)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused exchange (scatter GEMM + reduce/quant/gather): host protocol on CPU — buffer geometry, ownership of token rows,
+# ragged M, bias, hand-over of the QuantizedActivation to column-parallel consumers
+# ---------------------------------------------------------------------------------------------------------------
+class _EmulatedSymm:
+    """Stands in for symmetric memory on CPU: a local byte buffer, fake per-rank 'addresses' and no multicast."""
+
+    def __init__(self):
+        self.rank, self.world, self.group = dist.get_rank(), dist.get_world_size(), None
+
+    def alloc(self, nbytes, device):
+        self.buf = torch.full((nbytes,), 0x5A, dtype=torch.uint8)  # dirty: nothing may depend on stale contents ...
+        self.buf[-256:] = 0                                        # ... except the flag block, which starts at zero
+        return self.buf, [(r + 1) << 32 for r in range(self.world)], 0
+
+
+def _scatter_worker(rank, world, port, gs, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import qqq_oracle as O
+    from qqq_b200 import QuantizedActivation, ops, tp
+
+    K, N = 512, 256
+    backend = _EmulatedSymm()
+    ws = tp.ScatterWorkspace(max_tokens=16, max_features=N, backend=backend)
+
+    def dq(x):
+        q, s = O.dynamic_quant(x.numpy(), cuda_semantics=False)
+        return torch.from_numpy(q), torch.from_numpy(s)
+
+    def gemm_scatter(A, B, C, peer_partials, s1, s2, s3, workspace, prob_n, tp_rank, tp_world, tp_rows, max_par=16, sms=-1):
+        assert peer_partials == [((r + 1) << 32) + ws.off_part for r in range(world)] and (tp_rank, tp_world) == (rank, world)
+        part = torch.from_numpy(O.qqq_gemm_oracle(A.numpy(), B.numpy(), s1.numpy(), s2.numpy(),
+                                                  s3.numpy() if s3.numel() else None))
+        M = part.shape[0]
+        padded = torch.zeros(tp_rows * world, prob_n, dtype=torch.float16)
+        padded[:M] = part
+        allp = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(allp, padded)  # "every rank stores rows into their owner's slot"
+        slots = backend.buf[ws.off_part:ws.off_part + 2 * world * tp_rows * prob_n].view(torch.float16).view(world, tp_rows, prob_n)
+        for s in range(world):
+            slots[s] = allp[s][rank * tp_rows:(rank + 1) * tp_rows]
+
+    def reduce_quant(partials_ptr, a8_dst, a8_mc, s1_dst, s1_mc, h_out, bias, flags_ptr, peer_flags, tp_rank, tp_world,
+                     tp_rows, prob_m, prob_n, dev):
+        assert partials_ptr == ((rank + 1) << 32) + ws.off_part and a8_mc == 0 and s1_mc == 0
+        slots = backend.buf[ws.off_part:ws.off_part + 2 * world * tp_rows * prob_n].view(torch.float16).view(world, tp_rows, prob_n)
+        acc = torch.zeros(tp_rows, prob_n)
+        for s in range(world):
+            acc = acc + slots[s].float()
+        h = acc.half()
+        if bias is not None:
+            h = h + bias
+        my_rows = max(0, min(tp_rows, prob_m - rank * tp_rows))
+        if h_out is not None:
+            h_out[:my_rows] = h[:my_rows]
+        q, s1 = dq(h)
+        allq = [torch.empty_like(q) for _ in range(world)]
+        alls = [torch.empty_like(s1) for _ in range(world)]
+        dist.all_gather(allq, q)
+        dist.all_gather(alls, s1)
+        mpad = tp_rows * world
+        backend.buf[ws.off_a8:ws.off_a8 + mpad * prob_n].view(torch.int8).view(mpad, prob_n).copy_(torch.cat(allq))
+        backend.buf[ws.off_s1:ws.off_s1 + 4 * mpad].view(torch.float32).view(mpad, 1).copy_(torch.cat(alls))
+
+    ops.dynamic_quant = dq
+    ops.qqq_gemm_scatter = gemm_scatter
+    ops.tp_reduce_quant = reduce_quant
+    _, offs = tp.split_sizes(K, world, 128 if gs != -1 else 64)
+    ok = True
+    for it, M in enumerate((16, 5, 1, 9)):
+        p = O.make_problem(M, K, N, gs, seed=70 + it)
+        full = _full_module(p, K, N, gs)
+        if it % 2:
+            full.bias = torch.linspace(-1, 1, N).half()
+        shard = tp.shard_quant_linear(full, rank, world, "row")
+        mod = tp.ScatterRowParallelQuantLinear(shard, ws, keep_hidden=True)
+        x_loc = torch.from_numpy(p["x"][:, offs[rank]:offs[rank + 1]].copy())
+        # what it must equal: restatement on the per-rank partial outputs (bias-free), gathered
+        b = shard.bias
+        shard.bias = None
+        part = torch.from_numpy(_oracle_forward_cpu(shard, x_loc.numpy()))
+        shard.bias = b
+        parts = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(parts, part)
+        h_ref, a8_ref, s1_ref = tp.reference_reduce_quant(parts, mod.bias)
+        qa = mod(x_loc.reshape(1, M, -1))
+        rows = -(-M // world)
+        mine = slice(rank * rows, min(M, (rank + 1) * rows))
+        ok = ok and isinstance(qa, QuantizedActivation) and qa.lead == (1, M)
+        ok = ok and torch.equal(qa.q, a8_ref) and torch.equal(qa.s1, s1_ref) and torch.equal(mod.hidden, h_ref[mine])
+        # the consumer side: a column-parallel linear takes the QuantizedActivation as is
+        col = tp.ColumnParallelQuantLinear(tp.shard_quant_linear(_full_module(O.make_problem(M, N, 128, -1, seed=5), N, 128, -1),
+                                                                 rank, world, "column"))
+        seen = {}
+        ops.qqq_gemm = lambda A, B, C, D, s1, s2, s3, w, *a: seen.update(A=A, s1=s1, D=tuple(D.shape))
+        y = col(qa)
+        ok = ok and seen["A"] is qa.q and seen["s1"] is qa.s1 and tuple(y.shape) == (1, M, 64)
+    flags = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(bool(flags.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _oracle_forward_cpu(ql, x_np):
+    from oracle import qqq_oracle as O
+
+    A8, s1 = O.dynamic_quant(x_np, cuda_semantics=False)
+    s3 = ql.s_group.numpy() if ql.s_group.numel() else None
+    return O.qqq_gemm_oracle(A8, ql.B.numpy(), s1, ql.s_channel.numpy(), s3)
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_scatter_row_parallel_protocol_gloo(gs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_scatter_worker, args=(r, 2, port, gs, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    ok = q.get(timeout=240)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert ok, "fused exchange: geometry, ownership, bias or hand-over to the consumers wrong"
+
+
+def test_column_parallel_gather_with_uneven_shards_gloo():
+    """gather_output with N/64 not divisible by world (e.g. 11008 over 8 ranks) must not assume equal shards."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_uneven_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    ok = q.get(timeout=240)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert ok
+
+
+def _uneven_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import qqq_oracle as O
+    from qqq_b200 import tp
+
+    M, K, N = 5, 256, 192  # 3 blocks of 64 over 2 ranks: 128 + 64
+    p = O.make_problem(M, K, N, -1, seed=3)
+    full = _full_module(p, K, N, -1)
+    shard = tp.shard_quant_linear(full, rank, world, "column")
+    assert shard.outfeatures == (128 if rank == 0 else 64)
+    mod = tp.ColumnParallelQuantLinear(shard, gather_output=True)
+    mod.shard.forward = lambda x: torch.from_numpy(_oracle_forward_cpu(shard, x.numpy()))
+    y = mod(torch.from_numpy(p["x"]))
+    want = torch.from_numpy(_oracle_forward_cpu(full, p["x"]))
+    ok = torch.equal(y, want)
+    flags = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(bool(flags.item()))
+    dist.barrier()
+    dist.destroy_process_group()
