@@ -635,6 +635,8 @@ def gemm_sweep_tp(dev, peaks, rank, world, ws, max_over_ranks, K=8192, N=21760, 
 
     g = torch.Generator(device=dev).manual_seed(11 + rank)
     out = []
+    if ws is not None and (ws.max_tokens < max(Ms) or ws.max_features < N):  # the model's workspace is sized for the model
+        ws = tp.ScatterWorkspace(max(Ms), N, device=torch.device(dev) if isinstance(dev, str) and dev != "cpu" else None)
     n_loc = tp.split_sizes(N, world, 64)[0][rank]
     k_loc = tp.split_sizes(K, world, 128)[0][rank]
     int8_peak = 2.0 * peaks["bf16_tflops"]

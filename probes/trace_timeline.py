@@ -13,7 +13,7 @@ K = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
 N = int(sys.argv[4]) if len(sys.argv) > 4 else 21760
 dev = "cuda:0"
 lib = _lib.load()
-buf = torch.zeros(16 * 2048, dtype=torch.int64, device=dev)
+buf = torch.zeros(20 * 2048, dtype=torch.int64, device=dev)
 lib.qqq_trace_set.argtypes = [ctypes.c_void_p]
 assert lib.qqq_trace_set(buf.data_ptr()) == 0
 g = torch.Generator(device=dev).manual_seed(0)
@@ -29,7 +29,7 @@ for i in range(4):
     buf.zero_()
     qqq_b200.qqq_gemm(A, Bs[i % 3], C, D, s1, s2, s3, ws, -1, -1, -1, 16)
 torch.cuda.synchronize()
-t = buf.cpu().numpy().reshape(16, 2048)
+t = buf.cpu().numpy().reshape(20, 2048)
 t0 = t[12, 0]
 def rel(role):
     r = t[role].astype(np.int64)
@@ -44,6 +44,12 @@ stats("weights producer: issue duration (TR1-TR0)", P1 - P0)
 stats("weights producer: interval between stage grants", np.diff(P0))
 stats("mma: interval between unit issues", np.diff(M5))
 stats("mma: issue block duration (TR6-TR5)", M6 - M5)
+T16, T17, T18 = rel(16), rel(17), rel(18)
+if len(T16) and len(T16) == len(M5) and len(M6) == len(M5):
+    stats("mma: wait for tokens after previous issue block (TR16[i]-TR6[i-1])", (T16[1:] - M6[:-1]))
+    stats("mma: extra wait for unpacked weights (TR17-TR16)", T17 - T16)
+    n = min(len(T18), len(T16))
+    stats("tokens: TMA issue -> seen by the MMA warp (TR16-TR18)", T16[:n] - T18[:n])
 stats("epilogue: drain (TR8-TR7)", E8 - E7)
 stats("epilogue: total incl fixup (TR11-TR7)", E11 - E7)
 E13, E14 = rel(13), rel(14)

@@ -179,31 +179,41 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     const int per_tile = (M + *m_tiles - 1) / *m_tiles;
     return (per_tile + 15) / 16 * 16;
   };
+  auto kb_cycles = [](int n) {  // measured cycles per 128-deep k-block of a tile of n tokens (see below)
+    return n <= 128 ? 350.0 + 0.94 * n : (n <= 208 ? 470.0 + 1.625 * (n - 128) : 590.0);
+  };
   p.n_tok = tile_tokens(kMaxTok, &p.m_tiles);
   if (M > kMaxTok) {
-    // ... unless 128-token tiles fill the SMs so much better that they win despite their lower per-tile
-    // efficiency (measured ~0.85 of a 256-token tile): e.g. narrow tensor-parallel shards with fewer tiles than SMs.
-    // Whole-tile waves are compared; stream-K (below) only smooths the remainder.
-    int mt128 = 0;
-    const int nt128 = tile_tokens(128, &mt128);
-    const double waves256 = (double)((long long)p.m_tiles * p.n_tiles + sm_count - 1) / sm_count;
-    const double waves128 = (double)((long long)mt128 * p.n_tiles + sm_count - 1) / sm_count;
-    const double cost256 = (double)(long long)waves256 * p.n_tok, cost128 = (double)(long long)waves128 * nt128 / 0.85;
-    if (cost128 < 0.95 * cost256) {
-      p.n_tok = nt128;
-      p.m_tiles = mt128;
+    // ... unless smaller tiles fill the SMs so much better that they win despite their higher cost per token.
+    // Cost model from the round-2 measurements (profiles/r02/call_b, call_f): a 128-deep k-block of a tile costs
+    // ~350 + 0.94 * n_tok cycles up to 128 tokens, ~600 at 208 and ~590 at 256 (operand traffic L2 -> SM and hand-offs, not
+    // the 2 * n_tok cycles of the tensor pipe, bound the main loop); the accumulator drain costs ~29 cycles per token and
+    // is exposed once per tile when the accumulator is single-buffered (n_tok > kDbufMaxTok), once per CTA otherwise.
+    // Whole-tile waves are compared; stream-K (below) only smooths the remainder.  208 tokens = the largest tile that
+    // still leaves room for two accumulators and a 3-slot weight ring in TMEM (5 x 208 covers M = 1024).
+    double best = 0.0;
+    const int caps[3] = {kMaxTok, kDbufMaxTok, 128};
+    for (int ci = 0; ci < 3; ++ci) {
+      int mt = 0;
+      const int nt = tile_tokens(caps[ci], &mt);
+      const double waves = (double)(((long long)mt * p.n_tiles + sm_count - 1) / sm_count);
+      const double drain = 29.0 * nt + 100.0;
+      const bool dbuf = nt <= kDbufMaxTok;
+      double cost = waves * p.k_blocks * kb_cycles(nt) + (dbuf ? 1.0 : waves) * drain;
+      cost *= 1.0 + 0.03 * ci;  // near ties go to the larger tile (fewer re-reads of the weights)
+      if (ci == 0 || cost < best) {
+        best = cost;
+        p.n_tok = nt;
+        p.m_tiles = mt;
+      }
     }
   }
-  // Tuning overrides for experiments (not part of the ABI): QQQ_B200_NTOK caps the token tile, QQQ_B200_KSUB /
+  // Tuning overrides for experiments (not part of the ABI): QQQ_B200_NTOK sets the token-tile cap, QQQ_B200_KSUB /
   // QQQ_B200_NST force the stage depth in k and the token ring depth.
   static const int env_ntok = getenv("QQQ_B200_NTOK") ? atoi(getenv("QQQ_B200_NTOK")) : 0;
   static const int env_ksub = getenv("QQQ_B200_KSUB") ? atoi(getenv("QQQ_B200_KSUB")) : 0;
   static const int env_nst = getenv("QQQ_B200_NST") ? atoi(getenv("QQQ_B200_NST")) : 0;
-  if (env_ntok >= 16 && env_ntok <= kMaxTok && env_ntok % 16 == 0 && p.n_tok > env_ntok) {
-    p.m_tiles = (M + env_ntok - 1) / env_ntok;
-    const int pt = (M + p.m_tiles - 1) / p.m_tiles;
-    p.n_tok = (pt + 15) / 16 * 16;
-  }
+  if (env_ntok >= 16 && env_ntok <= kMaxTok && env_ntok % 16 == 0) p.n_tok = tile_tokens(env_ntok, &p.m_tiles);
   // several k-blocks per pipeline stage so that barrier round trips and the single-thread MMA issue loop are
   // amortised over >= 512 tensor-pipe cycles (an MMA of N tokens takes ~N/2 cycles, 4 per k-block)
   p.ksub = p.n_tok <= 64 ? 4 : (p.n_tok <= 128 ? 2 : 1);
@@ -306,21 +316,22 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
       // timelines (profiles/): a k-block costs 4 MMAs of max(48 issue, n_tok/2 pipe) cycles + ~48 of hand-off, and
       // not less than ~420 when the weights stream from DRAM (one token tile); a drain costs ~730 cycles per
       // 16-token chunk and epilogue warp + ~1400 fixed.
-      const double c_kb = 4.0 * (p.n_tok / 2 > 48 ? p.n_tok / 2 : 48) + 48.0;
+      const double c_kb = p.m_tiles > 1 ? (p.pair ? 552.0 : kb_cycles(p.n_tok))
+                                        : 4.0 * (p.n_tok / 2 > 48 ? p.n_tok / 2 : 48) + 48.0;
       const double t_u = p.ksub * (p.m_tiles == 1 && c_kb < 420.0 ? 420.0 : c_kb);
       const int n_epi = kWarps - kUnpackWarp0 - 4 * p.unpack_groups;
       const double t_d = 730.0 * ((p.n_tok / 16 + n_epi / 4 - 1) / (n_epi / 4)) + 1400.0;
       const bool dbuf = p.n_tok <= kDbufMaxTok;  // double-buffered accumulators: only the last drain of a CTA is exposed
       const long long waves = (tiles + grid - 1) / grid;
-#ifdef QQQ_DRAIN_HELPERS
-      // whole tiles are drained by 4 warps per TMEM quadrant (epilogue + unpack warps), split tiles by the epilogue warps
-      const double t_dw = 730.0 * ((p.n_tok / 16 + 3) / 4) + 1400.0;
-#else
       const double t_dw = t_d;
-#endif
       const double cost_whole = (double)waves * p.k_units * t_u + (dbuf ? 1.0 : (double)waves) * t_dw;
       const long long segs = (upc_all + p.k_units - 1) / p.k_units + 1;
-      const double cost_split = (double)upc_all * t_u + (dbuf ? 1.0 : (double)segs) * t_d;
+      // a CTA of a stream-K schedule publishes one partial tile and finishes another: int32 partials (2x the bytes of the
+      // fp16 output) go through L2 both ways and the finisher waits for its contributors — measured ~30 cycles per token
+      // and straddled tile on top of the plain drain (profiles/r02/call_b: stream-K lost 7 % at (1024, 4096, 11008) and
+      // (1024, 8192, 21760) where the older model, without this term, chose it)
+      const double t_fix = 30.0 * p.n_tok + 500.0;
+      const double cost_split = (double)upc_all * t_u + (dbuf ? 1.0 : (double)segs) * t_d + 2.0 * t_fix;
       if (env_split == 1 || cost_split < cost_whole) {
         a_tiles = tiles;
         a_upc = upc_all;
@@ -331,13 +342,13 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   p.a_units = (int)(a_tiles * p.k_units);
   p.a_upc = (int)a_upc;
   p.b_tiles = (int)(tiles - a_tiles);
-  p.b_tpc = (int)((p.b_tiles + grid - 1) / grid);
-  if (p.b_tiles > 0) {
-    const int used = (p.b_tiles + p.b_tpc - 1) / p.b_tpc;  // CTAs that get whole tiles
+  {
+    // whole tiles are dealt round-robin to min(grid, b_tiles) schedule indices; phase A uses ceil(a_units / a_upc)
+    const int used_b = p.b_tiles < grid ? p.b_tiles : grid;
     const int used_a = p.a_units > 0 ? (int)((p.a_units + a_upc - 1) / a_upc) : 0;
-    grid = used > used_a ? used : used_a;
-  } else {
-    grid = (int)((p.a_units + a_upc - 1) / a_upc);
+    grid = used_b > used_a ? used_b : used_a;
+    p.b_step = grid;
+    p.b_tpc = p.b_tiles > 0 ? (p.b_tiles + grid - 1) / grid : 0;
   }
   *grid_out = grid << p.pair;
   return QQQ_OK;
@@ -360,7 +371,7 @@ int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_coun
   if (rc != QQQ_OK) return rc;
   const int v[20] = {grid,      p.n_tok,   p.m_tiles, p.n_tiles,  p.k_blocks, p.ksub,    p.k_units,      p.a_tiles,
                      p.a_units, p.a_upc,   p.b_tiles, p.b_tpc,    p.stages_w, p.stages_t, p.unpack_groups,
-                     (int)qqq::gemm_smem_bytes(p), p.pair, 0, 0, 0};
+                     (int)qqq::gemm_smem_bytes(p), p.pair, p.b_step, 0, 0};
   for (int i = 0; i < 20; ++i) out[i] = v[i];
   return QQQ_OK;
 }
@@ -513,7 +524,7 @@ int qqq_tp_reduce_quant_sm100a(const void* partials, void* const* a8_dst, void* 
                                void* s1_multicast, void* h_out, const void* bias, void* flags, void* const* peer_flags,
                                int tp_rank, int tp_world, int tp_rows, int prob_m, int prob_n, int dev, void* stream_) {
   if (tp_world < 1 || tp_world > 8 || tp_rank < 0 || tp_rank >= tp_world || tp_rows < 1 ||
-      (long long)tp_rows * tp_world < prob_m || prob_m < 0 || prob_n <= 0 || prob_n % 8 != 0) {
+      (long long)tp_rows * tp_world < prob_m || prob_m < 0 || prob_n <= 0 || prob_n % 16 != 0) {
     set_err("tp_reduce_quant: bad geometry (rank=%d world=%d rows=%d m=%d n=%d)", tp_rank, tp_world, tp_rows, prob_m, prob_n);
     return QQQ_ERR_PROB_SHAPE;
   }

@@ -32,8 +32,8 @@
 //
 // Template variants of the one kernel: kPair (cluster of 2, cta_group::2: each CTA loads half of the token tile, the
 // leader issues UMMA M = 256 for both), kReduce (tensor-parallel row shards: the epilogue adds into a multicast D with
-// multimem.red instead of storing), kAcc (raw int32 accumulators out, for the bit-exact tensor-parallel mode); the
-// experiment builds -DQQQ_DBUF_MAX_TOK=208 and -DQQQ_DRAIN_HELPERS are described where they apply.
+// multimem.red instead of storing), kAcc (raw int32 accumulators out, for the bit-exact tensor-parallel mode); kOutScatter
+// (row goes to the partial-sum slot of the rank that owns it: the reduce-scatter half of the fused tensor-parallel exchange).
 #include "qqq_common.cuh"
 #include "qqq_gemm_sm100.h"
 
@@ -42,7 +42,7 @@ namespace qqq {
 // Optional per-role timeline for development (probes/trace_timeline.py builds a separate library with -DQQQ_TRACE;
 // the product build compiles these hooks away).
 #ifdef QQQ_TRACE
-__device__ unsigned long long* g_trace = nullptr;  // [16 roles][2048 events] of clock64()
+__device__ unsigned long long* g_trace = nullptr;  // [20 roles][2048 events] of clock64()
 #define QQQ_TR_INIT() unsigned long long* tr_ = (blockIdx.x == QQQ_TRACE_CTA) ? g_trace : nullptr
 #define QQQ_TR(role, idx)                                                            \
   do {                                                                               \
@@ -71,17 +71,22 @@ struct Ring {
 
 // Two-phase static schedule.  Phase A: the `a_tiles` remainder tiles that do not fill a whole wave are cut along K
 // into `a_upc`-unit slices, one slice per CTA (stream-K; a slice may straddle a tile boundary) — processed FIRST, so
-// their split-K fix-up overlaps the rest of the CTA's work.  Phase B: `b_tpc` whole tiles per CTA, processed last, so
-// the exposed tail of a CTA is a plain epilogue.  Every warp role walks the same segment list.
+// their split-K fix-up overlaps the rest of the CTA's work.  Phase B: whole tiles, dealt round-robin: CTA c takes tiles
+// a_tiles + c, a_tiles + c + grid, ...  Tile ids run token-tile-fastest (tile = mt + m_tiles * column), so at any moment
+// neighbouring CTAs work on the token tiles of the SAME weight column: its packed weights come from DRAM once and from
+// L2 for the other m_tiles - 1 readers (a CTA walking the token tiles of its own column one after the other re-read
+// them from DRAM: 2.4x the algorithmic traffic at M = 1024, N = 21760).  Every warp role walks the same segment list.
 struct Sched {
-  int KU, a_begin, a_end, n_a, b_first, n_b;
+  int KU, a_begin, a_end, n_a, b_first, b_step, n_b;
   __device__ Sched(const GemmParams& p, int cta) {
     KU = p.k_units;
     a_begin = min(cta * p.a_upc, p.a_units);
     a_end = min(a_begin + p.a_upc, p.a_units);
     n_a = a_end > a_begin ? (a_end - 1) / KU - a_begin / KU + 1 : 0;
-    b_first = p.a_tiles + cta * p.b_tpc;
-    n_b = max(0, min(p.b_tpc, p.a_tiles + p.b_tiles - b_first));
+    b_first = p.a_tiles + cta;
+    b_step = p.b_step;
+    const int total = p.a_tiles + p.b_tiles;
+    n_b = b_first < total ? (total - b_first + b_step - 1) / b_step : 0;
   }
   __device__ __forceinline__ int num_segments() const { return n_a + n_b; }
   __device__ __forceinline__ int num_units() const { return (a_end - a_begin) + n_b * KU; }
@@ -91,7 +96,7 @@ struct Sched {
       kb0 = i == 0 ? a_begin - tile * KU : 0;
       kb1 = min(KU, a_end - tile * KU);
     } else {
-      tile = b_first + (i - n_a);
+      tile = b_first + (i - n_a) * b_step;
       kb0 = 0;
       kb1 = KU;
     }
@@ -171,49 +176,6 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
   }
 }
 
-#ifdef QQQ_DRAIN_HELPERS
-// Experiment (-DQQQ_DRAIN_HELPERS; not in the default build).  The accumulator drain is latency-bound with two epilogue
-// warps per SM sub-partition (~730 cycles per 16-token chunk and warp against ~210 of issue), and it is exposed once per
-// tile when the accumulator is single-buffered (n_tok > kDbufMaxTok) and once per CTA otherwise.  The unpack warps sit on
-// the same sub-partitions and idle exactly then: a slot of the TMEM weight ring for unit (last unit of segment s) + NA
-// frees at the moment the MMA completes segment s.  So before unpacking that unit, every unpack warp takes its share of
-// the drain of segment s: a quadrant's chunks go round its 4 members (n_epi/4 epilogue warps, then the G unpack warps).
-// Static membership: every unpack warp waits for and arrives on the accumulator barriers of EVERY segment (so that its
-// parity waits stay in step), but converts and stores only where it pays: tiles this CTA finishes (whole tiles, and split
-// tiles for which it drew the last ticket: the epilogue hands ticket and "partials are published" over through
-// misc[2 + dbuf]), in single-buffer mode or for the CTA's last segment.  Publishing a partial stays with the epilogue.
-//
-// One 16-token chunk of this lane's channel, whole-tile case: TMEM -> fp32 * s2 * s1 -> fp16 -> warp-private smem tile
-// -> 16-byte row stores (same arithmetic and order as the epilogue warps' `process`).
-template <int kOut>
-__device__ __forceinline__ void helper_drain_chunk(const GemmParams& p, uint32_t (&r)[16], int m0, int mb, int rows,
-                                                   int col0 /* nt*128 + 32q */, bool q_ok, float s2v, unsigned short* stg,
-                                                   int lane, const int* __restrict__ partials, int others,
-                                                   size_t ticket_stride) {
-  // finisher of a split tile: add the partial tiles the other contributors published (block layout as in `process`)
-  for (int pp = 0; pp < others; ++pp) {
-    const int* __restrict__ src = partials + (size_t)pp * ticket_stride + (size_t)mb * kTileN;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] += (uint32_t)__ldcg(src + i * kTileN);
-  }
-  float s1v[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) s1v[i] = (m0 + mb + i < p.M) ? __ldg(p.s1 + m0 + mb + i) : 0.f;
-  unsigned short* sp = stg + lane;
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-    sp[i * 32] = __half_as_ushort(__float2half_rn((__int2float_rn((int)r[i]) * s2v) * s1v[i]));
-  __syncwarp();
-  if (q_ok) {
-    const int st_tok = lane >> 2, st_part = lane & 3;
-    const uint4* rp = reinterpret_cast<const uint4*>(stg) + lane;
-    const uint4 v0 = rp[0], v1 = rp[32];
-    if (mb + st_tok < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok) + (col0 + 8 * st_part), v0);
-    if (mb + st_tok + 8 < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok + 8) + (col0 + 8 * st_part), v1);
-  }
-  __syncwarp();
-}
-#endif
 
 // kAcc (qqq_gemm_acc_sm100a): the finished tile leaves as the raw int32 accumulators, row-major [M, N] int32, no scales —
 // for the bit-exact tensor-parallel mode (int32 partial sums are all-reduced, the scales applied once afterwards).
@@ -288,15 +250,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     if (lane < 2) {
       mbar_init(bar_dfull + 8 * lane, 1);
-#ifdef QQQ_DRAIN_HELPERS
-      mbar_init(bar_dempty + 8 * lane, (n_epi + 4 * G) << PAIR);  // the unpack warps arrive too (drain_share)
-#else
       mbar_init(bar_dempty + 8 * lane, n_epi << PAIR);
-#endif
     }
-#ifdef QQQ_DRAIN_HELPERS
-    if (lane == 0) misc[2] = misc[3] = 0;  // split-K ticket hand-off to the unpack warps, one word per accumulator buffer
-#endif
     mbar_fence_init();
     __syncwarp();
   }
@@ -379,6 +334,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================================== tokens producer ==================================
     grid_dependency_wait();  // A8 is produced by the preceding kernel (activation quant); weights are not
     Ring st(NST);
+#ifdef QQQ_TRACE
+    int t_count = 0;
+#endif
     for (int sg = 0; sg < n_seg; ++sg) {
       int tile, kb0, kb1;
       sched.segment(sg, tile, kb0, kb1);
@@ -386,6 +344,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_emptyt + 8 * st.idx, st.phase ^ 1);
         if (elect_one()) {
+          QQQ_TR(18, t_count++);
           const uint32_t full = bar_fullt + 8 * st.idx;
           if (!PAIR) {
             mbar_expect_tx(full, stage_t);
@@ -419,7 +378,14 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + dbuf * p.n_tok;
       for (int kb = kb0; kb < kb1; ++kb, ++ucount) {
+#ifdef QQQ_TRACE  // which operand the issuer waits for: tokens landed (16), then weights unpacked (17)
+        mbar_wait(bar_fullt + 8 * st.idx, st.phase);
+        if (lane == 0) QQQ_TR(16, ucount);
+        mbar_wait(bar_afull + 8 * as.idx, as.phase);
+        if (lane == 0) QQQ_TR(17, ucount);
+#else
         mbar_wait2(bar_fullt + 8 * st.idx, st.phase, bar_afull + 8 * as.idx, as.phase);
+#endif
         tc_fence_after();
         if (elect_one()) {
           QQQ_TR(5, ucount);
@@ -464,102 +430,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int turn = 0;  // which group owns the next sub-block
     int itn = 0;
     const int n_units = sched.num_units();
-#ifdef QQQ_DRAIN_HELPERS
-    // this warp's share of the drain of segment sg (see the comment above helper_drain_chunk)
-    unsigned short* stg_h = reinterpret_cast<unsigned short*>(sStage + (n_epi + (warp - kUnpackWarp0)) * kStageD);
-    bool h_dep_waited = false;
-    auto drain_share = [&](int sg) {
-      int tile, kb0, kb1;
-      sched.segment(sg, tile, kb0, kb1);
-      const int dbuf = sg % ndbuf;
-      const uint32_t dph = (sg / ndbuf) & 1;
-      const bool whole = (kb0 == 0 && kb1 == KU);
-      const bool where = ndbuf == 1 || sg == n_seg - 1;  // single-buffer mode, or the CTA's last (always exposed) drain
-      mbar_wait(bar_dfull + 8 * dbuf, dph);  // every phase is observed, helped or not: parity waits stay in step
-      tc_fence_after();
-      // split tile: the epilogue takes the ticket (and, as finisher, waits for the published partials) and hands the
-      // result over through misc[2 + dbuf] = (segment + 1) << 16 | ticket
-      const int parts = whole ? 1 : (tile * KU + KU - 1) / p.a_upc - (tile * KU) / p.a_upc + 1;
-      int ticket = 0;
-      if (!whole) {
-        uint32_t v = 0;
-        if (lane == 0) {
-          volatile uint32_t* hinfo = misc + 2 + dbuf;
-          while (((v = *hinfo) >> 16) != (uint32_t)(sg + 1)) {
-          }
-        }
-        v = __shfl_sync(0xffffffffu, v, 0);
-        ticket = (int)(v & 0xFFFFu);
-        __threadfence();  // reads of the published partials come after the epilogue's acquire
-      }
-      const bool finish = whole || ticket == parts - 1;
-      // publishers' partial stores stay with the epilogue warps (they announce them); raw-accumulator launches (kAcc) too
-      const bool help = where && finish && !kAcc;
-      if (help) {
-        if (!h_dep_waited) {  // s1 comes from the preceding kernel; D may still be in use by it
-          grid_dependency_wait();
-          h_dep_waited = true;
-        }
-        const int nt = nt_of(tile), mt = tile % p.m_tiles;
-        const int m0 = mt * p.n_tok;
-        const int rows = min(p.n_tok, p.M - m0);
-        const int n = nt * kTileN + 32 * q + lane;
-        const bool q_ok = nt * kTileN + 32 * q < p.N;
-        const float s2v = n < p.N ? __ldg(p.s2 + s2_position(n)) : 0.f;
-        const uint32_t tmem_d = tmem_base + dbuf * p.n_tok + ((uint32_t)(32 * q) << 16);
-        const size_t tile_ints = (size_t)p.n_tok * kTileN;
-        const int rtile = (tile << PAIR) + (int)rank;
-        const int* __restrict__ cbase = p.C + (size_t)rtile * tile_ints + 32 * q + lane;
-        const size_t ticket_stride = (size_t)(p.a_tiles << PAIR) * tile_ints;
-        const int others = whole ? 0 : parts - 1;
-        // software-pipelined like the epilogue warps: the TMEM load of the next chunk is in flight while this one is
-        // converted and stored
-        uint32_t ra[16], rb[16];
-        int mb = 16 * ((n_epi >> 2) + grp);
-        const int col0 = nt * kTileN + 32 * q;
-        if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
-        while (mb < rows) {
-          tmem_wait_ld();
-          const int mb2 = mb + 64;
-          if (mb2 < rows) tmem_ld_32x32b_x16(tmem_d + mb2, rb);
-          helper_drain_chunk<kOut>(p, ra, m0, mb, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
-          if (mb2 >= rows) break;
-          tmem_wait_ld();
-          mb = mb2 + 64;
-          if (mb < rows) tmem_ld_32x32b_x16(tmem_d + mb, ra);
-          helper_drain_chunk<kOut>(p, rb, m0, mb2, rows, col0, q_ok, s2v, stg_h, lane, cbase, others, ticket_stride);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR)
-          mbar_arrive_cluster(lead_dempty + 8 * dbuf);
-        else
-          mbar_arrive(bar_dempty + 8 * dbuf);
-      }
-    };
-    int h_seg = 0, h_end = 0;  // next segment to take a share of; number of units in segments [0, h_seg]
-    if (n_seg > 0) {
-      int t_, a_, b_;
-      sched.segment(0, t_, a_, b_);
-      h_end = b_ - a_;
-    }
-    auto drain_due = [&](int u) {  // segments whose last unit lies NA or more units behind unit u
-      while (h_seg < n_seg && h_end - 1 + NA <= u) {
-        drain_share(h_seg);
-        if (++h_seg < n_seg) {
-          int t_, a_, b_;
-          sched.segment(h_seg, t_, a_, b_);
-          h_end += b_ - a_;
-        }
-      }
-    };
-#endif
     for (int u = 0; u < n_units; ++u) {
-#ifdef QQQ_DRAIN_HELPERS
-      drain_due(u);
-#endif
       bool stage_ready = false, slot_ready = false;
       for (int sub = 0; sub < KSUB; ++sub, ++itn) {
         if (turn == grp) {
@@ -625,19 +496,12 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       st.advance();
       as.advance();
     }
-#ifdef QQQ_DRAIN_HELPERS
-    drain_due(0x3fffffff);  // the segments still outstanding when the units run out (always: the last one)
-#endif
   } else if (warp >= epi_warp0) {
     // ===================================== epilogue warps ===================================
     const int q = warp & 3;
     const int epi_tid = threadIdx.x - epi_warp0 * 32;
     const int eh = (warp - epi_warp0) >> 2;  // which of the n_epi/4 warps of this quadrant: takes every (n_epi/4)-th chunk
-#ifdef QQQ_DRAIN_HELPERS
-    int mstep = 16 * (n_epi >> 2);  // per segment: 64 where the unpack warps take their share (see drain_share)
-#else
     const int mstep = 16 * (n_epi >> 2);
-#endif
     // D leaves through a warp-private shared-memory tile: the warp holds a chunk as [channel = lane][16 tokens]; it
     // writes it as [16 tokens][32 channels] fp16 (row = 64 B, conflict-free), then every lane re-reads 16 B = 8
     // channels of one token and stores them: 2 vector stores per lane and chunk (each instruction covers 8 token
@@ -708,17 +572,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           named_bar_sync(1, n_epi_thr);
           __threadfence();  // order this thread's reads of the published partials after the acquire above
         }
-#ifdef QQQ_DRAIN_HELPERS
-        if (epi_tid == 0) {  // ticket (and "partials are published") for the unpack warps' share of this drain
-          __threadfence();
-          *reinterpret_cast<volatile uint32_t*>(misc + 2 + dbuf) = ((uint32_t)(seg + 1) << 16) | (uint32_t)ticket;
-        }
-#endif
       }
       const bool finish = whole || ticket == parts - 1;  // this CTA writes D for the tile
-#ifdef QQQ_DRAIN_HELPERS
-      mstep = (finish && !kAcc && (ndbuf == 1 || seg == n_seg - 1)) ? 64 : 16 * (n_epi >> 2);  // same rule as drain_share
-#endif
       const int others = (!whole && finish) ? parts - 1 : 0;  // published partial tiles the finisher adds
 
       // partial sums published by the other contributors, prefetched one 16-row chunk ahead (rows past `rows`

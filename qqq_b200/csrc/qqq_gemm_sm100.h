@@ -16,21 +16,15 @@ constexpr int kMaxASlots = 8;    // ring slots of 32*ksub columns each
 constexpr int kMaxStages = 16;
 constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
 // Token tiles up to this size get two accumulator buffers in TMEM (the drain of one tile overlaps the MMAs of the
-// next); the rest of the 512 columns is the unpacked-weight ring.  192 leaves 4 slots of 32 columns; an experiment
-// build with -DQQQ_DBUF_MAX_TOK=208 (3 slots; 5 x 208 tokens cover M = 1024) goes with QQQ_B200_NTOK=208.
+// next); the rest of the 512 columns is the unpacked-weight ring: 208 leaves 3 slots of 32 columns (5 x 208 tokens cover
+// M = 1024), 192 leaves 4.
 #ifndef QQQ_DBUF_MAX_TOK
-#define QQQ_DBUF_MAX_TOK 192
+#define QQQ_DBUF_MAX_TOK 208
 #endif
 constexpr int kDbufMaxTok = QQQ_DBUF_MAX_TOK;
 constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr int kStageD = 1024;          // one epilogue staging tile: 16 tokens x 32 channels fp16 (one warp's chunk)
-// Experiment build -DQQQ_DRAIN_HELPERS: the unpack warps take a share of the accumulator drain of whole tiles (see
-// drain_share in qqq_gemm_sm100.cu); every unpack / epilogue warp then needs a staging tile.
-#ifdef QQQ_DRAIN_HELPERS
-constexpr int kEpiStageBytes = 16 * kStageD;
-#else
 constexpr int kEpiStageBytes = 8 * kStageD;  // up to 8 epilogue warps
-#endif
 // warp roles: 0 weights TMA, 1 MMA (+TMEM alloc), 2 tokens TMA, 3 idle, then 4*G unpack warps (G groups x 4 TMEM
 // lane quadrants) and the remaining 16-4G warps as epilogue (G = 2: 8 epilogue warps, G = 3: 4).  24 warps
 // (G up to 4) were measured and did not help: all warps of a TMEM quadrant share one SM sub-partition, so extra
@@ -59,8 +53,9 @@ struct GemmParams {
   int a_tiles;  // tiles [0, a_tiles) are cut along K: CTA b owns phase-A units [b*a_upc, (b+1)*a_upc) of a_units
   int a_units;  // a_tiles * k_units
   int a_upc;    // >= 1 (1 when a_units == 0)
-  int b_tiles;  // tiles [a_tiles, a_tiles + b_tiles) are processed whole: CTA b owns b_tpc consecutive ones
-  int b_tpc;
+  int b_tiles;  // tiles [a_tiles, a_tiles + b_tiles) are processed whole, dealt round-robin: CTA b owns a_tiles + b + i*b_step
+  int b_tpc;    // ceil(b_tiles / b_step): whole tiles of the busiest CTA
+  int b_step;   // number of schedule indices (CTAs, or CTA pairs) the whole tiles are dealt to
   uint64_t hint_a, hint_b;  // L2 eviction policies for the token / weight streams
   int out_mode;             // 0: store D;  1: D is a multicast address and the epilogue adds into it (multimem.red);
                             // 2: D is int32 [M, N] and receives the raw accumulators (no scales);  3: scatter (below)

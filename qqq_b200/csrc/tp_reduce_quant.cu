@@ -27,6 +27,8 @@
 // between calls and CUDA-graph replays need no host state.  Every wait is bounded (kSpinTimeoutNs): a missing peer shows
 // up as flags[18] != 0 and garbage output, never as a hung GPU.
 #include "../../include/qqq_b200.h"
+#include <cstdlib>
+
 #include "quant_common.cuh"
 
 namespace qqq {
@@ -50,6 +52,9 @@ struct TpReduceParams {
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
@@ -76,9 +81,6 @@ __device__ __forceinline__ void multimem_st_16(void* mc, const uint4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
                : "memory");
-}
-__device__ __forceinline__ void multimem_st_8(void* mc, const uint2& v) {
-  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "r"(v.x), "r"(v.y) : "memory");
 }
 __device__ __forceinline__ void multimem_st_4(void* mc, uint32_t v) {
   asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
@@ -118,8 +120,10 @@ __device__ __forceinline__ uint4 sum_chunk(const uint4* __restrict__ part, size_
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// One CTA per owned token row (grid-stride); NCH 16-byte chunks of the row per thread stay in registers between the
-// reduction / max pass and the quantise pass (NCH == 0: any N, the second pass recomputes the sum).
+// One CTA per owned token row (grid-stride).  A thread owns NCH units of 16 consecutive channels (two 16-byte chunks of
+// fp16 in, ONE 16-byte piece of int8 out: NVLink moves 16-byte multicast stores at several times the rate of 8-byte
+// ones); the units stay in registers between the reduction / max pass and the quantise pass (NCH == 0: any N, the second
+// pass recomputes the sum).
 template <int NCH>
 __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpReduceParams p) {
   grid_launch_dependents();  // the next GEMM may run its prologue and prefetch its weights under this kernel
@@ -138,7 +142,8 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpRed
   }
   __syncthreads();
 
-  const int N8 = p.N >> 3;
+  const int N8 = p.N >> 3;    // 16-byte chunks of fp16 per row
+  const int N16 = p.N >> 4;   // units of 16 channels per row (N % 16 == 0)
   const int my_rows = max(0, min(p.rows_cap, p.M - p.rank * p.rows_cap));
   const size_t slot_stride16 = (size_t)p.rows_cap * N8;
   const uint4* part16 = reinterpret_cast<const uint4*>(p.part);
@@ -147,21 +152,30 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpRed
   for (int row = blockIdx.x; row < my_rows; row += gridDim.x) {
     const size_t row16 = (size_t)row * N8;
     const size_t grow = (size_t)p.rank * p.rows_cap + row;  // row of the gathered buffers
-    uint4 cache[NC];
+    uint4 cache[2 * NC];
     uint32_t m = 0;
+    auto load_unit = [&](int u, uint4& a, uint4& b) {
+      a = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u, bias16, 2 * u);
+      b = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u + 1, bias16, 2 * u + 1);
+      m = hmax2_u32(hmax2_u32(m, habs2_u32(a.x)), habs2_u32(a.y));
+      m = hmax2_u32(hmax2_u32(m, habs2_u32(a.z)), habs2_u32(a.w));
+      m = hmax2_u32(hmax2_u32(m, habs2_u32(b.x)), habs2_u32(b.y));
+      m = hmax2_u32(hmax2_u32(m, habs2_u32(b.z)), habs2_u32(b.w));
+    };
     if (NCH > 0) {
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
-        const int i = tid + j * kTpThreads;
-        cache[j] = (i < N8) ? sum_chunk(part16, slot_stride16, p.world, row16 + i, bias16, i) : make_uint4(0, 0, 0, 0);
-        m = hmax2_u32(hmax2_u32(m, habs2_u32(cache[j].x)), habs2_u32(cache[j].y));
-        m = hmax2_u32(hmax2_u32(m, habs2_u32(cache[j].z)), habs2_u32(cache[j].w));
+        const int u = tid + j * kTpThreads;
+        if (u < N16) {
+          load_unit(u, cache[2 * j], cache[2 * j + 1]);
+        } else {
+          cache[2 * j] = cache[2 * j + 1] = make_uint4(0, 0, 0, 0);
+        }
       }
     } else {
-      for (int i = tid; i < N8; i += kTpThreads) {
-        const uint4 v = sum_chunk(part16, slot_stride16, p.world, row16 + i, bias16, i);
-        m = hmax2_u32(hmax2_u32(m, habs2_u32(v.x)), habs2_u32(v.y));
-        m = hmax2_u32(hmax2_u32(m, habs2_u32(v.z)), habs2_u32(v.w));
+      for (int u = tid; u < N16; u += kTpThreads) {
+        uint4 a, b;
+        load_unit(u, a, b);
       }
     }
     __half2 mh = *reinterpret_cast<__half2*>(&m);
@@ -184,45 +198,59 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpRed
     }
     const bool fast = s > 0.f && s < __int_as_float(0x7F800000);
     const float rcp = __frcp_rn(s);
-    auto emit = [&](int i, const uint4& v) {
-      const uint2 q = fast ? make_uint2(quant4<true>(v.x, v.y, s, rcp), quant4<true>(v.z, v.w, s, rcp))
-                           : make_uint2(quant4<false>(v.x, v.y, s, rcp), quant4<false>(v.z, v.w, s, rcp));
-      const size_t off = grow * (size_t)p.N + (size_t)i * 8;
+    auto emit = [&](int u, const uint4& a, const uint4& b) {
+      const uint4 q = fast ? make_uint4(quant4<true>(a.x, a.y, s, rcp), quant4<true>(a.z, a.w, s, rcp),
+                                        quant4<true>(b.x, b.y, s, rcp), quant4<true>(b.z, b.w, s, rcp))
+                           : make_uint4(quant4<false>(a.x, a.y, s, rcp), quant4<false>(a.z, a.w, s, rcp),
+                                        quant4<false>(b.x, b.y, s, rcp), quant4<false>(b.z, b.w, s, rcp));
+      const size_t off = grow * (size_t)p.N + (size_t)u * 16;
       if (p.a8_mc != nullptr) {
-        multimem_st_8(p.a8_mc + off, q);
+        multimem_st_16(p.a8_mc + off, q);
       } else {
-        for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint2*>(p.a8_dst[r] + off) = q;
+        for (int r = 0; r < p.world; ++r) *reinterpret_cast<uint4*>(p.a8_dst[r] + off) = q;
       }
-      if (p.h_out != nullptr) reinterpret_cast<uint4*>(p.h_out)[row16 + i] = v;
+      if (p.h_out != nullptr) {
+        reinterpret_cast<uint4*>(p.h_out)[row16 + 2 * u] = a;
+        reinterpret_cast<uint4*>(p.h_out)[row16 + 2 * u + 1] = b;
+      }
     };
     if (NCH > 0) {
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
-        const int i = tid + j * kTpThreads;
-        if (i < N8) emit(i, cache[j]);
+        const int u = tid + j * kTpThreads;
+        if (u < N16) emit(u, cache[2 * j], cache[2 * j + 1]);
       }
     } else {
-      for (int i = tid; i < N8; i += kTpThreads) emit(i, sum_chunk(part16, slot_stride16, p.world, row16 + i, bias16, i));
+      for (int u = tid; u < N16; u += kTpThreads) {
+        uint4 a, b;
+        uint32_t keep = m;
+        load_unit(u, a, b);
+        m = keep;
+        emit(u, a, b);
+      }
     }
   }
 
   // arrive-2: the last CTA of this rank to finish tells every rank "my rows are delivered", then waits for the others,
-  // so that the kernel's completion means: all M rows of a8 / s1 are in place on this rank.
-  __threadfence_system();
+  // so that the kernel's completion means: all M rows of a8 / s1 are in place on this rank.  A system-scope fence costs
+  // 2-3 us on this fabric (profiles/r02/call_g), so there is exactly ONE on the critical path: every CTA fences its own
+  // stores (one thread, after the CTA-wide barrier: cumulativity covers the other threads' stores) BEFORE it bumps the
+  // finished-CTA counter; whoever sees the counter complete therefore knows that every CTA's rows have been performed
+  // at system scope and can raise the flags with plain system-scope stores.
   __syncthreads();
   if (tid == 0) {
+    __threadfence_system();
     const uint32_t done = atomicAdd(p.flags + 17, 1u);
     sh_last = (done == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
   if (sh_last) {
-    __threadfence_system();
     if (tid == 0) {
       p.flags[17] = 0;
       p.flags[16] = epoch;
     }
     if (tid < p.world) {
-      st_release_sys(p.peer_flags[tid] + 8 + p.rank, epoch);
+      st_relaxed_sys(p.peer_flags[tid] + 8 + p.rank, epoch);
       if (!wait_epoch(p.flags + 8 + tid, epoch)) atomicAdd(p.flags + 18, 1u);
     }
   }
@@ -262,13 +290,14 @@ cudaError_t launch_tp_reduce_quant(const void* part, void* const* a8_dst, void* 
   p.rows_cap = rows_cap;
   p.M = M;
   p.N = N;
+  // one CTA per SM measured best (fewer fences and counter bumps; rows are grid-strided); QQQ_B200_TPGRID overrides
+  static const int env_grid = getenv("QQQ_B200_TPGRID") ? atoi(getenv("QQQ_B200_TPGRID")) : 148;
   const int my_rows = M - rank * rows_cap < 0 ? 0 : (M - rank * rows_cap < rows_cap ? M - rank * rows_cap : rows_cap);
   // every rank launches at least one CTA: it still takes part in both flag exchanges
-  const int grid = my_rows < 1 ? 1 : (my_rows > 1184 ? 1184 : my_rows);
-  const int nch = (N / 8 + kTpThreads - 1) / kTpThreads;
+  const int grid = my_rows < 1 ? 1 : (my_rows > env_grid ? env_grid : my_rows);
+  const int nch = (N / 16 + kTpThreads - 1) / kTpThreads;  // 16-channel units per thread
   if (nch <= 1) return launch_tp<1>(p, grid, stream, pdl);
   if (nch <= 2) return launch_tp<2>(p, grid, stream, pdl);
-  if (nch <= 4) return launch_tp<4>(p, grid, stream, pdl);
   return launch_tp<0>(p, grid, stream, pdl);
 }
 

@@ -149,6 +149,7 @@ class QuantLinear(nn.Module):
         if trainable:
             raise NotImplementedError("Marlin does not support train.")
 
+        self.thread_config = list(_THREAD_CONFIG)  # attribute parity with the reference module (qlinear_marlin.py:66)
         self.infeatures = infeatures
         self.outfeatures = outfeatures
         self.group_size = group_size if group_size != -1 else infeatures
@@ -171,10 +172,27 @@ class QuantLinear(nn.Module):
         self.register_buffer(
             "reduce_buffer", torch.zeros((self.max_par * 16 * 4, outfeatures), dtype=torch.int), persistent=False
         )
+        self.wf = torch.tensor(list(range(0, 32, 4)), dtype=torch.int32).unsqueeze(0)  # qlinear_marlin.py:134 (unused there too)
         if bias:
             self.register_buffer("bias", torch.zeros((outfeatures), dtype=torch.half))
         else:
             self.bias = None
+        self._perm, self._scale_perm, self._scale_perm_single = self._get_perms()
+
+    def _get_perms(self):
+        """The reference's three permutations (qlinear_marlin.py:147-176), same types (int64 tensor of 1024, two lists),
+        in closed form: entry e = 32*lane + 8*j + p of `perm` addresses, inside a 16x64 weight tile flattened as
+        16*64 -> [k][n], the element k = 4*(lane%4) + r, n = 16*j + lane//4 + 8*blk, where (blk, r) = divmod(t, 4) and
+        t = [4,0,5,1,6,2,7,3][p] (per-channel) or [0,2,4,6,1,3,5,7][p] (per-group) is the nibble order inside a word.
+        `pack()` does not go through them (pack_int4_weights builds the words directly); they are exposed for code that
+        reads them off the reference module."""
+        e = torch.arange(1024, dtype=torch.int64)
+        lane, j, p_ = e // 32, (e // 8) % 4, e % 8
+        order = [0, 2, 4, 6, 1, 3, 5, 7] if self.per_group else [4, 0, 5, 1, 6, 2, 7, 3]
+        t = torch.tensor(order, dtype=torch.int64)[p_]
+        perm = 16 * (4 * (lane % 4) + t % 4) + lane // 4 + 8 * (t // 4) + 256 * j
+        sp64, sp32 = _scale_perm_positions("cpu")
+        return perm, sp64.tolist(), sp32.tolist()
 
     def _apply(self, fn):
         # keep scale dtypes pinned across .half()/.to(dtype) exactly like qlinear_marlin.py:141-145

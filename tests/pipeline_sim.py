@@ -61,9 +61,8 @@ def segments(p, cta):
     if a_end > a_begin:
         for t in range(a_begin // KU, (a_end - 1) // KU + 1):
             segs.append((t, max(a_begin - t * KU, 0), min(KU, a_end - t * KU)))
-    b_first = p["a_tiles"] + cta * p["b_tpc"]
-    n_b = max(0, min(p["b_tpc"], p["a_tiles"] + p["b_tiles"] - b_first))
-    segs += [(b_first + i, 0, KU) for i in range(n_b)]
+    total = p["a_tiles"] + p["b_tiles"]
+    segs += [(t, 0, KU) for t in range(p["a_tiles"] + cta, total, p["b_step"])]  # whole tiles: round-robin
     return segs
 
 
@@ -72,7 +71,7 @@ class Deadlock(AssertionError):
 
 
 class CtaSim:
-    def __init__(self, plan, cta, M, seed=0, helpers=False, dbuf_max_tok=192, twin=False, leader=None):
+    def __init__(self, plan, cta, M, seed=0, helpers=False, dbuf_max_tok=208, twin=False, leader=None):
         """twin=True: CTA pair approximated by doubling this CTA's arrivals on the shared barriers.
         leader=<CtaSim>: this object is the PEER CTA (rank 1) of a faithfully modelled pair (see PairSim)."""
         self.p, self.rng, self.helpers = plan, (leader.rng if leader else random.Random(seed)), helpers
@@ -323,7 +322,7 @@ class CtaSim:
                     assert self.drained.get((sg, q, c), 0) == 1, f"segment {sg} quadrant {q} chunk {c}: drained {self.drained.get((sg, q, c), 0)}x"
 
 
-def PairSim(plan, cta, M, seed=0, helpers=False, dbuf_max_tok=192):
+def PairSim(plan, cta, M, seed=0, helpers=False, dbuf_max_tok=208):
     """Both CTAs of a pair (cluster of 2, cta_group::2) on one clock: each has its own weight ring and unpack / epilogue
     warps and loads half of the token tile; the leader's MMA warp consumes both and its commits release both."""
     lead = CtaSim(plan, cta, M, seed=seed, helpers=helpers, dbuf_max_tok=dbuf_max_tok)

@@ -120,6 +120,28 @@ def test_errors_match_reference_conditions():
         qqq_b200.qqq_gemm(t["A8"], t["B"], C, D, t["s1"], t["s2"], t["s3"], ws, 96, 128, -1, 16)
 
 
+def _weights_on_gpu(K, N, per_group, seed, dev):
+    """Full-size shapes: packing 178 M weights through the numpy oracle costs ~10 s per case, so nibbles are drawn and
+    packed on the device with the product's vectorised packer (bit-identical to the oracle's and the reference's pack():
+    tests/test_pack.py) and decoded to int8 by a torch restatement of oracle.w8_per_channel / w8_per_group."""
+    from qqq_b200 import pack_int4_weights
+
+    g = torch.Generator(device=dev).manual_seed(seed)
+    if per_group:
+        w = torch.randint(0, 16, (K, N), device=dev, generator=g, dtype=torch.int32)
+        s3_nat = (torch.rand(K // 128, N, device=dev, generator=g) * 12 + 2).half()  # |(v-8)*s| <= 8*14 = 112
+        exact = (w.double() - 8.0) * s3_nat.double().repeat_interleave(128, dim=0) + 1152.0  # exact in f64
+        byte = (exact.half().view(torch.int16) & 0xFF) ^ 0x80  # one RNE rounding == the kernel's single fp16 FMA
+        W8 = byte.to(torch.uint8).view(torch.int8)
+        s3 = s3_nat.reshape(K // 128, N // 64, 8, 8).transpose(-1, -2).reshape(K // 128, N).contiguous()  # scale_perm
+    else:
+        w = torch.randint(-8, 8, (K, N), device=dev, generator=g, dtype=torch.int32)
+        W8 = (w * 16).to(torch.int8)
+        s3 = torch.zeros(0, dtype=torch.float16, device=dev)
+    B = pack_int4_weights(w, per_group)
+    return B, s3, W8
+
+
 def check_vs_int_mm(M, K, N, gs):
     """Shapes too big for the numpy oracle in seconds are checked against an independent exact path on the GPU:
     torch._int_mm on oracle-decoded int8 weights (size-independent property: the accumulator is an exact integer),
@@ -128,34 +150,76 @@ def check_vs_int_mm(M, K, N, gs):
     g = torch.Generator(device="cpu").manual_seed(M + 17)
     rng = np.random.default_rng(M + K + N)
     per_group = gs != -1
-    w = rng.integers(0, 16, size=(K, N)) if per_group else rng.integers(-8, 8, size=(K, N))
-    B = O.pack_B(w, per_group)
     s2_nat = (rng.random(N).astype(np.float32) + 0.5) * 1e-3
     s2 = O.permute_s_channel(s2_nat)
-    if per_group:
-        s3_nat = (rng.random((K // 128, N)) * 12 + 2).astype(np.float16)  # |(v-8)*s| <= 8*14 = 112
-        s3 = O.permute_s_group(s3_nat)
-        W8 = O.w8_per_group(w, s3_nat)
-    else:
-        s3 = np.zeros((0,), np.float16)
-        W8 = O.w8_per_channel(w & 0xF)
     A8 = torch.randint(-128, 128, (M, K), dtype=torch.int8, generator=g)
     s1 = (torch.rand((M, 1), generator=g) + 0.5) * 1e-2
-    p = dict(A8=A8.numpy(), B=B, s1=s1.numpy(), s2=s2, s3=s3)
-    D, C, ws = run_gemm(p, N)
+    if K * N > 40e6:
+        import qqq_b200
+
+        B, s3, W8 = _weights_on_gpu(K, N, per_group, M + K + N, dev)
+        C = torch.zeros((16 * 64, N), dtype=torch.int32, device=dev)
+        ws = torch.zeros(N // 128 * 16, dtype=torch.int32, device=dev)
+        Dt = torch.full((M, N), float("nan"), dtype=torch.float16, device=dev)
+        qqq_b200.qqq_gemm(A8.to(dev), B, C, Dt, s1.to(dev), torch.from_numpy(s2).to(dev), s3, ws, -1, -1, -1, 16)
+        torch.cuda.synchronize()
+        D = Dt.cpu().numpy()
+    else:
+        w = rng.integers(0, 16, size=(K, N)) if per_group else rng.integers(-8, 8, size=(K, N))
+        B = O.pack_B(w, per_group)
+        if per_group:
+            s3_nat = (rng.random((K // 128, N)) * 12 + 2).astype(np.float16)  # |(v-8)*s| <= 8*14 = 112
+            s3 = O.permute_s_group(s3_nat)
+            W8 = O.w8_per_group(w, s3_nat)
+        else:
+            s3 = np.zeros((0,), np.float16)
+            W8 = O.w8_per_channel(w & 0xF)
+        W8 = torch.from_numpy(W8.astype(np.int8)).to(dev)
+        p = dict(A8=A8.numpy(), B=B, s1=s1.numpy(), s2=s2, s3=s3)
+        D, C, ws = run_gemm(p, N)
     Mp = max(32, (M + 7) // 8 * 8)  # _int_mm wants M > 16 and multiples of 8
     Ap = torch.zeros((Mp, K), dtype=torch.int8, device=dev)
     Ap[:M] = A8.to(dev)
-    acc = torch._int_mm(Ap, torch.from_numpy(W8.astype(np.int8)).to(dev))[:M]
+    acc = torch._int_mm(Ap, W8)[:M]
     ref = ((acc.float() * torch.from_numpy(s2_nat).to(dev)[None, :]) * s1.to(dev)).half().cpu().numpy()
     assert np.array_equal(bits(D), bits(ref))
     assert int(ws.abs().sum()) == 0
 
 
-@pytest.mark.parametrize("M,gs", [(1, -1), (16, 128), (128, -1), (1024, 128), (4096, -1)])
+@pytest.mark.parametrize("gs", [-1, 128])
+@pytest.mark.parametrize("M", [1, 16, 128, 1024, 4096])
 def test_full_size_sweep_shape_vs_int_mm(M, gs):
-    """BASELINE configs[4]: the sweep shape K=8192, N=21760 at every M of the sweep."""
+    """BASELINE configs[4]: the sweep shape K=8192, N=21760 at every M of the sweep, both modes (all 10 benchmarked points)."""
     check_vs_int_mm(M, 8192, 21760, gs)
+
+
+# Planner overrides are read once per process (static in qqq_c_api.cu), so the forced-mode runs happen in a child process:
+# CTA pairs wherever the shape allows them (QQQ_B200_PAIR=1), stream-K over all tiles wherever scratch allows it
+# (QQQ_B200_SPLIT=1), whole tiles only (QQQ_B200_SPLIT=0), and the smaller token tiles (QQQ_B200_NTOK).
+FORCED_SHAPES = [(1024, 8192, 21760, -1), (1024, 8192, 21760, 128), (1024, 4096, 11008, -1), (2048, 4096, 4096, 128),
+                 (1024, 11008, 4096, -1), (512, 4096, 4096, -1), (300, 2048, 1024, 128), (4096, 8192, 21760, -1)]
+
+
+@pytest.mark.skipif(os.environ.get("QQQ_FORCED_INNER") != "1", reason="runs inside test_forced_planner_modes' child process")
+@pytest.mark.parametrize("M,K,N,gs", FORCED_SHAPES)
+def test_forced_inner(M, K, N, gs):
+    check_vs_int_mm(M, K, N, gs)
+
+
+@pytest.mark.parametrize("env", [{"QQQ_B200_PAIR": "1"}, {"QQQ_B200_SPLIT": "1"}, {"QQQ_B200_SPLIT": "0", "QQQ_B200_PAIR": "0"},
+                                 {"QQQ_B200_NTOK": "208"}, {"QQQ_B200_NTOK": "128", "QQQ_B200_SPLIT": "1"}],
+                         ids=["pair", "split", "whole-nopair", "ntok208", "ntok128-split"])
+def test_forced_planner_modes(env):
+    """Every benchmarked configuration family is bit-checked, not only the planner's default choice per shape."""
+    import subprocess
+    import sys
+
+    e = dict(os.environ, QQQ_FORCED_INNER="1", **env)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-k", "test_forced_inner", "-m", "gpu", "-x",
+                          "-q", "-p", "no:cacheprovider"], env=e, capture_output=True, text=True, timeout=900,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
+    assert f"{len(FORCED_SHAPES)} passed" in out.stdout, out.stdout[-500:]
 
 
 MODEL_SHAPES = [

@@ -38,6 +38,37 @@ def test_pack_bit_identical_to_reference(path):
     assert tuple(ql.reduce_buffer.shape) == tuple(g["reduce_buffer_shape"])
     assert ql.B.dtype == torch.int32 and ql.s_channel.dtype == torch.float32 and ql.s_group.dtype == torch.float16
     assert int(ql.workspace.abs().sum()) == 0 and int(ql.reduce_buffer.abs().sum()) == 0
+    # the reference instance's permutation attributes (qlinear_marlin.py:139,147-176), stored with the fixture
+    assert np.array_equal(ql._perm.numpy(), g["perm"]) and ql._scale_perm == g["scale_perm"].tolist()
+    assert ql._scale_perm_single == g["scale_perm_single"].tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", PACK, ids=os.path.basename)
+def test_pack_on_the_device_is_bit_identical_to_reference(path):
+    """`pack()` runs on CUDA tensors (the reference packs on the CPU with numpy, qlinear_marlin.py:181-262)
+    and must produce the reference's packed buffers bit for bit; the packed module then runs where it was packed."""
+    g = np.load(path)
+    dev = torch.device("cuda:0")
+    K, N, gs = int(g["K"]), int(g["N"]), int(g["group_size"])
+    lin = torch.nn.Linear(K, N, bias=True).half().to(dev)
+    lin.weight.data = torch.from_numpy(g["weight_fq"]).to(dev)
+    lin.bias.data = torch.from_numpy(g["bias"]).to(dev)
+    ql = QuantLinear(4, gs, K, N, bias=True).to(dev)
+    s_extra = torch.from_numpy(g["s_extra"]).to(dev) if "s_extra" in g.files else None
+    ql.pack(lin, torch.from_numpy(g["scales"]).to(dev), s_extra)
+    assert ql.B.is_cuda and ql.s_channel.is_cuda
+    assert np.array_equal(ql.B.cpu().numpy(), g["B"])
+    assert np.array_equal(ql.s_channel.cpu().numpy(), g["s_channel"])
+    assert np.array_equal(ql.s_group.cpu().numpy().view(np.uint16), g["s_group"].view(np.uint16))
+    assert np.array_equal(ql.bias.cpu().numpy().view(np.uint16), g["packed_bias"].view(np.uint16))
+    # ... and the module packed on the device computes what the oracle computes from the reference's packed buffers
+    x = torch.randn(9, K, device=dev).half()
+    y = ql(x)
+    A8, s1 = O.dynamic_quant(x.cpu().numpy(), cuda_semantics=True)
+    s3 = g["s_group"] if g["s_group"].size else None
+    want = torch.from_numpy(O.qqq_gemm_oracle(A8, g["B"], s1, g["s_channel"], s3)) + torch.from_numpy(g["packed_bias"])
+    assert np.array_equal(y.cpu().numpy().view(np.uint16), want.numpy().view(np.uint16))
 
 
 @pytest.mark.parametrize("pg", [False, True])

@@ -34,18 +34,6 @@ def default_lib():
     return _lib.load()
 
 
-@pytest.fixture(scope="session")
-def helpers_lib(tmp_path_factory):
-    """Planner of the -DQQQ_DRAIN_HELPERS experiment build (larger epilogue staging area -> other ring depths)."""
-    out = tmp_path_factory.mktemp("variant") / "libqqq_b200_helpers.so"
-    subprocess.check_call([sys.executable, os.path.join(ROOT, "probes", "build_variant.py"), str(out), "-DQQQ_DRAIN_HELPERS"],
-                          stdout=subprocess.DEVNULL)
-    lib = ctypes.CDLL(str(out))
-    lib.qqq_b200_plan.argtypes = [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_int)]
-    lib.qqq_b200_plan.restype = ctypes.c_int
-    return lib
-
-
 def _ctas(p):
     n = p["grid"] >> p["pair"]
     return sorted({0, 1 % n, n // 2, n - 1})
@@ -71,12 +59,6 @@ def _simulate(lib, M, N, K, gs, sms, helpers, seeds=(0, 1)):
 @pytest.mark.parametrize("sms", [148, 37])
 def test_default_kernel_protocol(default_lib, M, N, K, gs, sms):
     _simulate(default_lib, M, N, K, gs, sms, helpers=False)
-
-
-@pytest.mark.parametrize("M,N,K,gs", SHAPES)
-@pytest.mark.parametrize("sms", [148, 37])
-def test_drain_helper_variant_protocol(helpers_lib, M, N, K, gs, sms):
-    _simulate(helpers_lib, M, N, K, gs, sms, helpers=True)
 
 
 def test_model_catches_the_round1_ring_depth_bug(default_lib):

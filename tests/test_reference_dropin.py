@@ -171,3 +171,19 @@ def test_pack_of_extreme_and_clamped_values_matches_the_reference(reference_modu
         a, b = getattr(ref, name), getattr(ours, name)
         assert a.shape == b.shape and torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a.view(torch.int16) if a.dtype == torch.half else a,
                                                     b.view(torch.int32) if b.dtype == torch.float32 else b.view(torch.int16) if b.dtype == torch.half else b), name
+
+
+@pytest.mark.parametrize("gs", [-1, 128])
+def test_permutation_attributes_match_the_reference_module(reference_module, gs):
+    """`_get_perms()`, `_perm`, `_scale_perm`, `_scale_perm_single`, `wf`, `thread_config` (qlinear_marlin.py:66,134,139,147-176):
+    same values and types as the reference instance (ours come from a closed form, not from the reference's loops)."""
+    import qqq_b200
+
+    mod, _ = reference_module
+    a, b = mod.QuantLinear(4, gs, 256, 256, False), qqq_b200.QuantLinear(4, gs, 256, 256, False)
+    assert torch.equal(a._perm, b._perm) and a._perm.dtype == b._perm.dtype
+    assert a._scale_perm == b._scale_perm and a._scale_perm_single == b._scale_perm_single
+    assert isinstance(b._scale_perm, list) and isinstance(b._scale_perm_single, list)
+    assert a.thread_config == b.thread_config and torch.equal(a.wf, b.wf)
+    pa, pb = a._get_perms(), b._get_perms()
+    assert torch.equal(pa[0], pb[0]) and pa[1:] == pb[1:]

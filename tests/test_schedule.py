@@ -10,7 +10,7 @@ import pytest
 from qqq_b200 import _lib
 
 KEYS = ["grid", "n_tok", "m_tiles", "n_tiles", "k_blocks", "ksub", "k_units", "a_tiles", "a_units", "a_upc", "b_tiles",
-        "b_tpc", "stages_w", "stages_t", "unpack_groups", "smem_bytes", "pair", "_r1", "_r2", "_r3"]
+        "b_tpc", "stages_w", "stages_t", "unpack_groups", "smem_bytes", "pair", "b_step", "_r2", "_r3"]
 
 
 def plan(M, N, K, gs=-1, sms=148, max_par=16):
@@ -29,9 +29,8 @@ def segments(p, cta):
     if a_end > a_begin:
         for t in range(a_begin // KU, (a_end - 1) // KU + 1):
             segs.append((t, max(a_begin - t * KU, 0), min(KU, a_end - t * KU)))
-    b_first = p["a_tiles"] + cta * p["b_tpc"]
-    n_b = max(0, min(p["b_tpc"], p["a_tiles"] + p["b_tiles"] - b_first))
-    segs += [(b_first + i, 0, KU) for i in range(n_b)]
+    total = p["a_tiles"] + p["b_tiles"]
+    segs += [(t, 0, KU) for t in range(p["a_tiles"] + cta, total, p["b_step"])]  # whole tiles: round-robin
     return segs
 
 
@@ -83,8 +82,7 @@ def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
                 seen[(t, kb)] = cta
             contributors.setdefault(t, []).append(cta)
     assert len(seen) == tiles * KU, "some unit is never produced"
-    # CTAs beyond the grid must have no work
-    assert segments(p, p["grid"]) == []
+    assert p["b_step"] == p["grid"]  # whole tiles are dealt to exactly the CTAs that are launched
     # split tiles: the kernel's contributor count formula, scratch capacity and lock words
     # C (64*max_par rows of N int32) holds compact [n_tok][128] partial tiles, block = ticket * a_tiles + tile
     tile_ints = p["n_tok"] * 128
