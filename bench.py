@@ -263,6 +263,20 @@ def forward_chain_merged(mlayers, h, world):
     return h
 
 
+def forward_chain_merged_scatter(mlayers, x):
+    """forward_chain_scatter with q/k/v and gate/up of each rank's shards merged into one GEMM each."""
+    import qqq_b200
+    from qqq_b200 import ops
+
+    qa = qqq_b200.QuantizedActivation(*ops.dynamic_quant(x))
+    for m in mlayers:
+        qkv = m["qkv"](qa)
+        qa = m["o"](qkv[:, : m["qkv"].split_sizes[0]])
+        gu = m["gate_up"](qa)
+        qa = m["down"](gu[:, : m["gate_up"].split_sizes[0]])
+    return mlayers[-1]["down"].hidden
+
+
 def gemm_only_chain(layers, qin):
     """The GEMM launches of a step alone, on pre-quantised inputs (for the roofline figure of the dominant kernel)."""
     import qqq_b200
@@ -864,9 +878,12 @@ def main():
 
     # the same weights with q/k/v and gate/up merged: 4 activation quants + 4 GEMMs per layer
     ms_mrg = None
-    if not args.no_merged and tp_mode in ("single", "nccl"):
+    if not args.no_merged and tp_mode in ("single", "nccl", "scatter"):
         mlayers = merge_layers(layers)
-        graphed_mrg = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
+        if tp_mode == "scatter":
+            graphed_mrg = qgraph.capture(lambda x: forward_chain_merged_scatter(mlayers, x), x_dev)
+        else:
+            graphed_mrg = qgraph.capture(lambda x: forward_chain_merged(mlayers, x, world), x_dev)
         ms_mrg = max_over_ranks(timed(lambda: graphed_mrg(x_dev), args.steps, args.warmup, barrier))
         del graphed_mrg, mlayers
 

@@ -51,6 +51,15 @@ int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* 
                     int dev, void* stream /* cudaStream_t */, int thread_k, int thread_n, int sms, int max_par);
 
 /*
+ * qqq_gemm_sm100a with the bias add of QuantLinear.forward (QQQ/gptq/qlinear/qlinear_marlin.py:286-288, an eager `D + bias`
+ * there) folded into the epilogue: D = fp16(fp16((acc * s2) * s1) + bias[n]) — the add is an fp16 add on the rounded
+ * output, so the bits equal the reference's two-step result.  bias fp16 [N] in natural channel order, or NULL.
+ */
+int qqq_gemm_bias_sm100a(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2, const void* s3,
+                         const void* bias, int prob_m, int prob_n, int prob_k, void* workspace, int groupsize, int dev,
+                         void* stream /* cudaStream_t */, int sms, int max_par);
+
+/*
  * Tensor-parallel row shards (new work: the reference has no tensor parallelism): the same GEMM on this
  * rank's K-shard, but every 16-byte piece of the output is ADDED (fp16, `multimem.red`) into `D_multicast` instead of
  * stored.  `D_multicast` is the multicast address (cuMulticast* / NVLS, e.g. torch symmetric memory's `multicast_ptr`) of
@@ -124,7 +133,7 @@ long long qqq_b200_launch_count(void);
 
 /* The tiling / schedule the library would use for a problem on `sm_count` SMs (pure host computation, no GPU):
  * out[20] = {grid, n_tok, m_tiles, n_tiles, k_blocks, ksub, k_units, a_tiles, a_units, a_upc, b_tiles, b_tpc,
- *            stages_w, stages_t, unpack_groups, smem_bytes, pair, b_step, 0, 0}.  Tiles are 128 channels x n_tok tokens; a
+ *            stages_w, stages_t, unpack_groups, smem_bytes, pair, b_step, compact, 0}.  Tiles are 128 channels x n_tok tokens; a
  * SCHEDULED tile is one tile, or with pair = 1 two adjacent 128-channel tiles handled by a CTA pair (cluster of 2,
  * cta_group::2; grid is then even and CTAs 2c, 2c+1 walk the schedule of index c).  Scheduled tile id = mt +
  * m_tiles * column; a unit is `ksub` 128-deep k-blocks of one scheduled tile.  Scheduled tiles [0,a_tiles) are cut

@@ -15,6 +15,7 @@ LIB_PATH = _HERE / "libqqq_b200.so"
 # Every symbol include/qqq_b200.h declares.
 SYMBOLS = (
     "qqq_gemm_sm100a",
+    "qqq_gemm_bias_sm100a",
     "qqq_gemm_reduce_sm100a",
     "qqq_gemm_acc_sm100a",
     "qqq_gemm_scatter_sm100a",
@@ -51,6 +52,8 @@ def load() -> ctypes.CDLL:
     vp, ci = ctypes.c_void_p, ctypes.c_int
     lib.qqq_gemm_sm100a.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci]
     lib.qqq_gemm_sm100a.restype = ci
+    lib.qqq_gemm_bias_sm100a.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, ci]
+    lib.qqq_gemm_bias_sm100a.restype = ci
     lib.qqq_gemm_reduce_sm100a.argtypes = list(lib.qqq_gemm_sm100a.argtypes)
     lib.qqq_gemm_reduce_sm100a.restype = ci
     lib.qqq_gemm_acc_sm100a.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, ci]

@@ -165,6 +165,18 @@ __device__ __forceinline__ __half* out_row(const GemmParams& p, int m) {
     return p.D + (size_t)m * p.N;
   }
 }
+__device__ __forceinline__ uint4 hadd2_x4(const uint4& a, const uint4& b) {
+  uint4 o;
+  const uint32_t* pa = &a.x;
+  const uint32_t* pb = &b.x;
+  uint32_t* po = &o.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __hadd2(*reinterpret_cast<const __half2*>(pa + i), *reinterpret_cast<const __half2*>(pb + i));
+    po[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return o;
+}
 template <int kOut>
 __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
   if constexpr (kOut == kOutReduce) {
@@ -179,8 +191,13 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
 
 // kAcc (qqq_gemm_acc_sm100a): the finished tile leaves as the raw int32 accumulators, row-major [M, N] int32, no scales —
 // for the bit-exact tensor-parallel mode (int32 partial sums are all-reduced, the scales applied once afterwards).
-template <bool GROUPED, bool kPair, int kOut = kOutStore>
-__global__ void __launch_bounds__(kThreads, 1)
+// kNW = warps per CTA: kWarps (20; one CTA per SM with the whole shared memory and all 512 TMEM columns), or kWarpsCompact
+// (12: one unpack group + 4 epilogue warps, half of the shared memory, 256 TMEM columns) for decode-size token tiles, so
+// that TWO CTAs fit an SM: with programmatic dependent launch the CTAs of the NEXT kernel in the stream move in while this
+// kernel's last CTAs are still draining and run their prologue, weight TMAs and unpack under that tail — at decode a GEMM
+// is a ~10 us kernel of which ~4 us were launch, prologue, first DRAM round trip and the last drain.
+template <bool GROUPED, bool kPair, int kOut = kOutStore, int kNW = kWarps>
+__global__ void __launch_bounds__(32 * kNW, kNW == kWarps ? 1 : 2)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
   constexpr bool kAcc = kOut == kOutAcc;
@@ -193,7 +210,8 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // one tile overlaps the MMAs of the next), then the ring of unpacked weight tiles (one slot = one unit = 32*KSUB columns)
   const int ndbuf = p.n_tok <= kDbufMaxTok ? 2 : 1;
   const int tmem_a0 = ndbuf * p.n_tok;
-  const int NA = min(kMaxASlots, (512 - tmem_a0) / (32 * KSUB));
+  const int tmem_cols = kNW == kWarps ? 512 : 256;
+  const int NA = min(kMaxASlots, (tmem_cols - tmem_a0) / (32 * KSUB));
   // CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent 128-channel tiles of the same token tile
   // and the same k-range; one MMA instruction of the leader (rank 0) drives both tensor cores (UMMA M = 256), every
   // CTA loads only its half of the token tile (rows [rank*n_tok/2, ...)), halving the L2->SM token traffic per SM.
@@ -203,7 +221,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int tok_bytes = tok_rows * 128;               // one sub-block of tokens in this CTA's shared memory
   const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
   uint8_t* sStage = smem;                   // epilogue staging: one [16][32] fp16 tile per epilogue warp
-  uint8_t* sT = sStage + kEpiStageBytes;
+  uint8_t* sT = sStage + epi_stage_bytes(kNW != kWarps);
   uint8_t* sW = sT + NST * stage_t;
   uint8_t* sS = sW + NSW * stage_w;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSW * stage_s);
@@ -221,7 +239,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.unpack_groups;                 // 2 or 3 groups of unpack warps (host policy in qqq_c_api.cu)
   const int epi_warp0 = kUnpackWarp0 + 4 * G;    // warps [epi_warp0, kWarps) drain the accumulators
-  const int n_epi = kWarps - epi_warp0;          // 8 or 4 epilogue warps
+  const int n_epi = kNW - epi_warp0;             // 8 or 4 epilogue warps
   const int n_epi_thr = 32 * n_epi;
   const int KU = p.k_units;  // units per tile
   const Sched sched(p, (int)blockIdx.x >> PAIR);  // the schedule is over (super-)tiles: both CTAs of a pair walk it
@@ -297,9 +315,9 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
   if (warp == 1) {
     if (PAIR)
-      tmem_alloc_pair(smem_u32(&misc[0]), 512);
+      tmem_alloc_pair(smem_u32(&misc[0]), tmem_cols);
     else
-      tmem_alloc(smem_u32(&misc[0]), 512);
+      tmem_alloc(smem_u32(&misc[0]), tmem_cols);
   }
   tc_fence_before();
   if (PAIR)
@@ -533,6 +551,12 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int parts = whole ? 1 : (tile * KU + KU - 1) / p.a_upc - (tile * KU) / p.a_upc + 1;
       float s2v = 0.f;
       if constexpr (!kAcc) s2v = n_ok ? __ldg(p.s2 + s2_position(n)) : 0.f;  // kAcc: no scales (s1 / s2 are null)
+      // optional bias, added in fp16 after the fp16 rounding of D like the reference's eager `D + bias`
+      // (qlinear_marlin.py:287) — one rounding more, same bits.  Applied on the store side, where a lane holds 8 channels
+      // of a token row: 8 half2 adds per chunk instead of 16 scalar ones inside the conversion loop.
+      const bool has_bias = p.bias != nullptr;
+      uint4 bias_v = make_uint4(0, 0, 0, 0);
+      if (has_bias && q_ok) bias_v = __ldg(reinterpret_cast<const uint4*>(p.bias + nt * kTileN + 32 * q + 8 * st_part));
       // Partial tiles of split-K live in C as compact [n_tok][128] int32 blocks, block index =
       // (ticket * a_tiles + tile): a chunk's 16 rows are 512 B apart, so the 16 stores / loads of a lane use one base
       // register and immediate offsets (no serial address chain), and each of them is one full 128-byte line per warp.
@@ -624,10 +648,20 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (epi_tid == 0) QQQ_TR(15, echunk);
           if (q_ok) {  // the whole 32-channel quadrant is inside N (N % 64 == 0) or outside
             const uint4* rp = reinterpret_cast<const uint4*>(stg) + lane;  // row st_tok, part st_part
-            const uint4 v0 = rp[0], v1 = rp[32];                            // rows st_tok and st_tok + 8
+            uint4 v0 = rp[0], v1 = rp[32];                                  // rows st_tok and st_tok + 8
+            if (has_bias) {
+              v0 = hadd2_x4(v0, bias_v);
+              v1 = hadd2_x4(v1, bias_v);
+            }
             const int col = nt * kTileN + 32 * q + 8 * st_part;
-            if (mb + st_tok < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok) + col, v0);
-            if (mb + st_tok + 8 < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok + 8) + col, v1);
+            if constexpr (kOut == kOutScatter) {
+              if (mb + st_tok < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok) + col, v0);
+              if (mb + st_tok + 8 < rows) emit_d<kOut>(out_row<kOut>(p, m0 + mb + st_tok + 8) + col, v1);
+            } else {
+              __half* dp = p.D + (size_t)(m0 + mb + st_tok) * p.N + col;
+              if (mb + st_tok < rows) emit_d<kOut>(dp, v0);
+              if (mb + st_tok + 8 < rows) emit_d<kOut>(dp + (size_t)8 * p.N, v1);
+            }
           }
           __syncwarp();  // the tile is rewritten by the next chunk
         } else {
@@ -690,45 +724,54 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (threadIdx.x == 0) QQQ_TR(12, 1);
   if (warp == 1) {
     if (PAIR)
-      tmem_dealloc_pair(tmem_base, 512);
+      tmem_dealloc_pair(tmem_base, tmem_cols);
     else
-      tmem_dealloc(tmem_base, 512);
+      tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
 }  // namespace
 
 size_t gemm_smem_bytes(const GemmParams& p) {
-  return 1024 + kEpiStageBytes + (size_t)p.stages_t * p.ksub * (p.n_tok >> p.pair) * 128 +
+  return 1024 + epi_stage_bytes(p.compact) + (size_t)p.stages_t * p.ksub * (p.n_tok >> p.pair) * 128 +
          (size_t)p.stages_w * p.ksub * (kStageB + kStageS) +
          8 * (2 * p.stages_w + 2 * p.stages_t + 2 * kMaxASlots + 4) + 16 + 4 * kMaxTok;
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
-  static bool attr_set[10][64] = {};  // the opt-in shared-memory attribute is per device
+  static bool attr_set[16][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
   if (p.out_mode != kOutStore && p.pair) return cudaErrorInvalidValue;  // the planner never pairs these launches
   if (p.out_mode < 0 || p.out_mode > kOutScatter) return cudaErrorInvalidValue;
-  const int variant = p.out_mode != kOutStore ? 2 + 2 * p.out_mode + (grouped ? 1 : 0) : (grouped ? 1 : 0) + (p.pair ? 2 : 0);
-  auto kern = variant == 0 ? qqq_gemm_kernel<false, false>
-            : variant == 1 ? qqq_gemm_kernel<true, false>
-            : variant == 2 ? qqq_gemm_kernel<false, true>
-            : variant == 3 ? qqq_gemm_kernel<true, true>
-            : variant == 4 ? qqq_gemm_kernel<false, false, kOutReduce>
-            : variant == 5 ? qqq_gemm_kernel<true, false, kOutReduce>
-            : variant == 6 ? qqq_gemm_kernel<false, false, kOutAcc>
-            : variant == 7 ? qqq_gemm_kernel<true, false, kOutAcc>
-            : variant == 8 ? qqq_gemm_kernel<false, false, kOutScatter>
-                           : qqq_gemm_kernel<true, false, kOutScatter>;
+  if (p.compact && (p.pair || p.out_mode == kOutAcc)) return cudaErrorInvalidValue;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const GemmParams);
+  constexpr int C = kWarpsCompact;
+  static const Kern table[16] = {
+      qqq_gemm_kernel<false, false>, qqq_gemm_kernel<true, false>, qqq_gemm_kernel<false, true>, qqq_gemm_kernel<true, true>,
+      qqq_gemm_kernel<false, false, kOutReduce>, qqq_gemm_kernel<true, false, kOutReduce>,
+      qqq_gemm_kernel<false, false, kOutAcc>, qqq_gemm_kernel<true, false, kOutAcc>,
+      qqq_gemm_kernel<false, false, kOutScatter>, qqq_gemm_kernel<true, false, kOutScatter>,
+      qqq_gemm_kernel<false, false, kOutStore, C>, qqq_gemm_kernel<true, false, kOutStore, C>,
+      qqq_gemm_kernel<false, false, kOutReduce, C>, qqq_gemm_kernel<true, false, kOutReduce, C>,
+      qqq_gemm_kernel<false, false, kOutScatter, C>, qqq_gemm_kernel<true, false, kOutScatter, C>};
+  const int g1 = grouped ? 1 : 0;
+  const int variant = p.compact ? (p.out_mode == kOutStore ? 10 : p.out_mode == kOutReduce ? 12 : 14) + g1
+                      : p.out_mode != kOutStore ? 2 + 2 * p.out_mode + g1
+                                                : g1 + (p.pair ? 2 : 0);
+  const Kern kern = table[variant];
   if (dev < 0 || dev >= 64 || !attr_set[variant][dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         p.compact ? kCompactSmemBytes : kMaxSmemBytes);
+    if (e != cudaSuccess) return e;
+    // the whole L1/shared array as shared memory: the compact variant needs it for two CTAs per SM
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[variant][dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(32 * (p.compact ? kWarpsCompact : kWarps));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

@@ -99,6 +99,23 @@ def qqq_gemm(A, B, C, D, s1, s2, s3, workspace, thread_k=-1, thread_n=-1, sms=-1
         raise RuntimeError(f"qqq_gemm_sm100a failed (rc={err}): {_lib.last_error()}")
 
 
+def qqq_gemm_bias(A, B, C, D, s1, s2, s3, workspace, bias, max_par=16, sms=-1):
+    """`qqq_gemm` with QuantLinear.forward's bias add folded into the epilogue (qqq_gemm_bias_sm100a): same checks, same bits
+    as `qqq_gemm(...)` followed by the reference's eager `D + bias`."""
+    prob_m, prob_n, prob_k, groupsize = check_gemm_args(A, B, C, D, s1, s2, s3, workspace, max_par)
+    if not A.is_cuda:
+        raise RuntimeError("qqq_gemm_bias: tensors must be CUDA tensors (qqq_b200 has no CPU path).")
+    if bias.dtype != torch.float16 or bias.numel() != prob_n or not bias.is_contiguous() or bias.device != A.device:
+        raise RuntimeError("qqq_gemm_bias: bias must be a contiguous float16 [n] tensor on the device of A.")
+    dev = A.get_device()
+    err = _lib.load().qqq_gemm_bias_sm100a(
+        _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(s1), _ptr(s2), _ptr(s3) if s3.numel() else None, _ptr(bias),
+        prob_m, prob_n, prob_k, _ptr(workspace), groupsize, dev, torch.cuda.current_stream(dev).cuda_stream, sms, max_par,
+    )
+    if err != 0:
+        raise RuntimeError(f"qqq_gemm_bias_sm100a failed (rc={err}): {_lib.last_error()}")
+
+
 def qqq_gemm_reduce(A, B, C, d_multicast_ptr: int, s1, s2, s3, workspace, prob_n: int, max_par=16, sms=-1):
     """Row-shard GEMM whose epilogue ADDS its fp16 output into the multicast address `d_multicast_ptr` (an fp16 [M, prob_n]
     buffer replicated on every rank of the tensor-parallel group) instead of storing it: qqq_gemm_reduce_sm100a in

@@ -272,11 +272,15 @@ class QuantLinear(nn.Module):
                 if _ActQuantCache.enabled:
                     _ActQuantCache.put(A, (quant_A, s1))
         D = torch.empty(quant_A.shape[0], self.outfeatures, dtype=torch.float16, device=quant_A.device)
-        mul(quant_A, self.B, self.reduce_buffer, D, s1, self.s_channel, self.s_group, self.workspace,
-            max_par=self.max_par)
-        D = D.reshape(out_shape)
-        D = D + self.bias if self.bias is not None else D
-        return D
+        if self.bias is not None and quant_A.shape[0] > 0:
+            # the reference adds the bias with an eager op after the GEMM (qlinear_marlin.py:286-288); here it rides in the
+            # GEMM's epilogue (same fp16 add on the rounded output, same bits)
+            ops.qqq_gemm_bias(quant_A, self.B, self.reduce_buffer, D, s1, self.s_channel, self.s_group, self.workspace,
+                              self.bias, self.max_par)
+        else:
+            mul(quant_A, self.B, self.reduce_buffer, D, s1, self.s_channel, self.s_group, self.workspace,
+                max_par=self.max_par)
+        return D.reshape(out_shape)
 
 
 def merge_quant_linears(mods) -> QuantLinear:

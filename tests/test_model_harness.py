@@ -59,8 +59,13 @@ def oracle_backend(monkeypatch):
         ref = O.qqq_gemm_oracle(A.numpy(), B.numpy(), s1.numpy(), s2.numpy(), s3.numpy() if s3.numel() else None)
         D.copy_(torch.from_numpy(ref))
 
+    def gemm_bias(A, B, C, D, s1, s2, s3, workspace, bias, max_par=16, sms=-1):
+        ops.qqq_gemm(A, B, C, D, s1, s2, s3, workspace, -1, -1, sms, max_par)  # looked up at call time: tests wrap it
+        D += bias  # fp16 add on the rounded output, like the kernel's epilogue and the reference's eager op
+
     monkeypatch.setattr(ops, "dynamic_quant", dq)
     monkeypatch.setattr(ops, "qqq_gemm", gemm)
+    monkeypatch.setattr(ops, "qqq_gemm_bias", gemm_bias)
 
 
 # ---------------------------------------------------------------------------------------------------------------

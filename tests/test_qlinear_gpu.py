@@ -42,6 +42,22 @@ def test_forward_keeps_leading_dims_and_bias():
     assert torch.equal(y, y0 + 0.5)
 
 
+@pytest.mark.parametrize("M,K,N,gs", [(1, 4096, 1024, 128), (33, 1024, 320, -1), (300, 2048, 384, 128), (1024, 512, 1152, -1),
+                                      (32, 4096, 4096, 128), (2, 256, 64, -1)])
+def test_bias_in_the_epilogue_equals_the_reference_two_step_result(M, K, N, gs):
+    """`D + bias` (qlinear_marlin.py:286-288) folded into the GEMM epilogue: identical bits to the oracle's D followed by an
+    fp16 add, over whole-tile, stream-K (finisher) and compact-variant schedules, ragged M and N % 128 == 64."""
+    p = O.make_problem(M, K, N, gs, seed=M + N)
+    ql = _module(p, K, N, gs)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(N)).half()
+    ql.bias = bias.cuda()
+    y = ql(torch.from_numpy(p["x"]).cuda())
+    A8, s1 = O.dynamic_quant(p["x"], cuda_semantics=True)
+    want = torch.from_numpy(O.qqq_gemm_oracle(A8, p["B"], s1, p["s2"], p["s3"])) + bias
+    assert torch.equal(y.cpu().view(torch.int16), want.view(torch.int16))
+    assert int(ql.workspace.abs().sum()) == 0
+
+
 @pytest.mark.parametrize("gs", [-1, 128])
 def test_merged_linears_bit_identical_to_separate(gs):
     import qqq_b200
