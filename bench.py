@@ -202,16 +202,33 @@ def _all_reduce_after(mod, y, world):
         dist.all_reduce(y)
 
 
+OVERLAP = True  # linears that share their input (q/k/v, gate/up) are issued on forked streams (qqq_b200.graph.fork_join)
+
+
+def _together(mods, x):
+    """The linears of `mods` on the same input: one after the other, or (OVERLAP) as parallel branches of the graph."""
+    from qqq_b200 import graph as qgraph
+
+    if not OVERLAP:
+        return [m(x) for m in mods]
+    import qqq_b200
+    from qqq_b200 import ops, qlinear
+
+    if qlinear._ActQuantCache.enabled and not isinstance(x, qqq_b200.QuantizedActivation):
+        # the shared quantisation (what the activation-quant cache does implicitly) is issued BEFORE the fork, so that
+        # every branch depends on it through the fork event
+        x2 = x.reshape(-1, x.shape[-1]).half()
+        x = qqq_b200.QuantizedActivation(*ops.dynamic_quant(x2), tuple(x.shape[:-1]))
+    return qgraph.fork_join([(lambda m=m: m(x)) for m in mods])
+
+
 def forward_chain(layers, h, world):
     """The reference's module structure: 7 separate linears per layer, called in the model's order."""
     for m in layers:
-        q = m["q"](h)
-        m["k"](h)
-        m["v"](h)
+        q = _together([m["q"], m["k"], m["v"]], h)[0]
         o = m["o"](q)
         _all_reduce_after(m["o"], o, world)
-        g = m["gate"](o)
-        m["up"](o)
+        g = _together([m["gate"], m["up"]], o)[0]
         d = m["down"](g)
         _all_reduce_after(m["down"], d, world)
         h = d
@@ -227,12 +244,9 @@ def forward_chain_scatter(layers, x):
 
     qa = qqq_b200.QuantizedActivation(*ops.dynamic_quant(x))
     for m in layers:
-        q = m["q"](qa)
-        m["k"](qa)
-        m["v"](qa)
+        q = _together([m["q"], m["k"], m["v"]], qa)[0]
         qa = m["o"](q)
-        g = m["gate"](qa)
-        m["up"](qa)
+        g = _together([m["gate"], m["up"]], qa)[0]
         qa = m["down"](g)
     return layers[-1]["down"].hidden
 
@@ -482,12 +496,9 @@ def decode_g128(dev, peaks, steps, warmup):
 
     def chain(h):
         for m in layers:
-            q = m["q"](h)
-            m["k"](h)
-            m["v"](h)
+            q = _together([m["q"], m["k"], m["v"]], h)[0]
             o = m["o"](q)
-            g = m["gate"](o)
-            m["up"](o)
+            g = _together([m["gate"], m["up"]], o)[0]
             h = m["down"](g)
         return h
 
@@ -759,10 +770,14 @@ def main():
     ap.add_argument("--no-full", action="store_true", help="skip the whole-model (HF Llama forward) section")
     ap.add_argument("--no-70b", action="store_true", help="N > 1: skip the Llama-2-70B section (configs[3])")
     ap.add_argument("--no-tp-sweep", action="store_true", help="N > 1: skip the tensor-parallel GEMM sweep")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="issue q/k/v and gate/up strictly one after the other instead of as parallel branches of the graph")
     ap.add_argument("--aux-budget", type=float, default=300.0, help="seconds the auxiliary sections may take in total")
     args = ap.parse_args()
     if args.fused_allreduce:
         args.tp_mode = "reduce"
+    global OVERLAP
+    OVERLAP = not args.no_overlap
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
     M = MODEL["seq"] * MODEL["batch"]
@@ -932,7 +947,8 @@ def main():
                          api="qqq_b200.graph.capture(QuantLinear chain); eager QuantLinear.forward loop: "
                              f"{ms_eager:.3f} ms/step"),
                 gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
-                launch_mode="cuda-graph replay of the per-step launches",
+                launch_mode="cuda-graph replay of the per-step launches" + (
+                    "; q/k/v and gate/up are parallel branches of the graph (forked streams)" if OVERLAP else ""),
                 merged=None if ms_mrg is None else dict(
                     ms_per_step=round(ms_mrg, 4), value=round(M / (ms_mrg * 1e-3), 1),
                     note="same weights with q/k/v and gate/up merged by concatenating their packed tensors "

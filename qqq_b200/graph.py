@@ -12,6 +12,42 @@ import torch
 from .qlinear import _ActQuantCache
 
 
+_side_streams = {}
+
+
+def fork_join(thunks):
+    """Run independent launches (linears that consume the same activation: q/k/v, gate/up) on forked streams and join them
+    again: `[t() for t in thunks]`, but thunks[1:] are issued on side streams that wait for everything issued so far, and the
+    current stream waits for them before it goes on.  Captured into a CUDA graph this becomes parallel branches: the CTAs
+    of the second GEMM move onto SMs as the first one's CTAs retire instead of waiting for its last drain and completion,
+    and GEMMs smaller than the machine (tensor-parallel shards, decode) run side by side.  Each thunk must use its own
+    scratch (every QuantLinear owns its reduce buffer and lock words; `model.share_scratch` gives that up)."""
+    thunks = list(thunks)
+    if len(thunks) <= 1 or not torch.cuda.is_available():
+        return [t() for t in thunks]
+    dev = torch.cuda.current_device()
+    cur = torch.cuda.current_stream(dev)
+    pool = _side_streams.setdefault(dev, [])
+    while len(pool) < len(thunks) - 1:
+        pool.append(torch.cuda.Stream(device=dev))
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    outs = [None] * len(thunks)
+    joins = []
+    for i in range(1, len(thunks)):
+        s = pool[i - 1]
+        s.wait_event(fork)
+        with torch.cuda.stream(s):
+            outs[i] = thunks[i]()
+            e = torch.cuda.Event()
+            e.record(s)
+            joins.append(e)
+    outs[0] = thunks[0]()
+    for e in joins:
+        cur.wait_event(e)
+    return outs
+
+
 class GraphedCallable:
     def __init__(self, fn, example_input: torch.Tensor, warmup: int = 2, pool=None):
         self.static_in = example_input.clone()

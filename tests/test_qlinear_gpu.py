@@ -84,3 +84,35 @@ def test_graph_capture_replays_the_same_bits():
     out = g(x).clone()
     out2 = g(x * 1).clone()
     assert torch.equal(eager, out) and torch.equal(eager, out2)
+
+
+def test_fork_join_branches_give_the_serial_bits_in_a_graph():
+    """q/k/v-style linears on forked streams (graph.fork_join) inside a captured graph: same bits as one after the other,
+    replay after replay, with the shared quantisation issued before the fork."""
+    import qqq_b200
+    from qqq_b200 import graph, ops
+
+    K = 1024
+    ps = [O.make_problem(48, K, n, gs, seed=s) for n, gs, s in ((256, -1, 1), (128, -1, 2), (384, -1, 3))]
+    mods = [_module(p, K, p["B"].shape[1] // 2, -1) for p in ps]
+    tail = _module(O.make_problem(48, 256, 128, -1, seed=9), 256, 128, -1)
+    x = torch.from_numpy(ps[0]["x"]).cuda()
+
+    def serial(t):
+        qa = qqq_b200.QuantizedActivation(*ops.dynamic_quant(t))
+        ys = [m(qa) for m in mods]
+        return torch.cat(ys + [tail(ys[0])], dim=-1)
+
+    def forked(t):
+        qa = qqq_b200.QuantizedActivation(*ops.dynamic_quant(t))
+        ys = graph.fork_join([(lambda m=m: m(qa)) for m in mods])
+        return torch.cat(ys + [tail(ys[0])], dim=-1)
+
+    want = serial(x).clone()
+    assert torch.equal(forked(x), want)  # eager, on real side streams
+    g = graph.capture(forked, x)
+    for _ in range(3):
+        assert torch.equal(g(x), want)
+    x2 = x * 0.5
+    assert torch.equal(g(x2), serial(x2))
+    assert all(int(m.workspace.abs().sum()) == 0 for m in mods)
