@@ -133,7 +133,7 @@ long long qqq_b200_launch_count(void);
 
 /* The tiling / schedule the library would use for a problem on `sm_count` SMs (pure host computation, no GPU):
  * out[20] = {grid, n_tok, m_tiles, n_tiles, k_blocks, ksub, k_units, a_tiles, a_units, a_upc, b_tiles, b_tpc,
- *            stages_w, stages_t, unpack_groups, smem_bytes, pair, b_step, compact, 0}.  Tiles are 128 channels x n_tok tokens; a
+ *            stages_w, stages_t, unpack_groups, smem_bytes, pair, b_step, 0, 0}.  Tiles are 128 channels x n_tok tokens; a
  * SCHEDULED tile is one tile, or with pair = 1 two adjacent 128-channel tiles handled by a CTA pair (cluster of 2,
  * cta_group::2; grid is then even and CTAs 2c, 2c+1 walk the schedule of index c).  Scheduled tile id = mt +
  * m_tiles * column; a unit is `ksub` 128-deep k-blocks of one scheduled tile.  Scheduled tiles [0,a_tiles) are cut

@@ -166,7 +166,7 @@ bool reference_shape_ok(int n, int k, int thread_k, int thread_n) {
 // Pure host-side planning (no CUDA calls): tiling, pipeline depths and the two-phase schedule for a problem on
 // `sm_count` SMs.  Exported as qqq_b200_plan() so the schedule can be checked exhaustively on a CPU-only machine.
 int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool has_scratch, qqq::GemmParams& p,
-              int* grid_out, bool allow_pair = true, bool allow_compact = true) {
+              int* grid_out, bool allow_pair = true) {
   using namespace qqq;
   p.M = M;
   p.N = N;
@@ -222,15 +222,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   // several k-blocks per pipeline stage so that barrier round trips and the single-thread MMA issue loop are
   // amortised over >= 512 tensor-pipe cycles (an MMA of N tokens takes ~N/2 cycles, 4 per k-block)
   p.ksub = p.n_tok <= 64 ? 4 : (p.n_tok <= 128 ? 2 : 1);
-  // Compact variant for decode-size token tiles (see qqq_gemm_kernel): 12 warps, half of the shared memory, 256 TMEM columns
-  // — two CTAs per SM, so that the next kernel's CTAs (programmatic dependent launch) move in and prefetch under this
-  // kernel's tail.  256 columns hold two accumulators and a ring of (256 - 2 n_tok) / (32 ksub) unpacked-weight slots:
-  // two k-blocks per stage while that leaves three slots, else one.  QQQ_B200_COMPACT=0/1 overrides.
-  static const int env_compact = getenv("QQQ_B200_COMPACT") ? atoi(getenv("QQQ_B200_COMPACT")) : -1;
-  p.compact = (allow_compact && p.n_tok <= 64 && p.m_tiles == 1 && env_compact != 0) ? 1 : 0;
-  if (p.compact) p.ksub = (256 - 2 * p.n_tok) / 64 >= 3 ? 2 : 1;
   if (env_ksub == 1 || env_ksub == 2 || env_ksub == 4) p.ksub = env_ksub;
-  if (p.compact && (256 - 2 * p.n_tok) / (32 * p.ksub) < 2) p.ksub = 1;
   while (p.ksub > 1 && p.k_blocks < p.ksub) p.ksub >>= 1;
   p.k_units = (p.k_blocks + p.ksub - 1) / p.ksub;
   // CTA pairs (cluster of 2, cta_group::2, see qqq_gemm_sm100.cu): two CTAs share a token tile and each loads half of
@@ -238,12 +230,11 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   // N = 21760), neutral at ~2 tiles per SM, slower when there is at most one tile per SM or the tiles are small.
   // QQQ_B200_PAIR=0/1 overrides the policy (1: wherever the shape allows it).
   static const int env_pair = getenv("QQQ_B200_PAIR") ? atoi(getenv("QQQ_B200_PAIR")) : -1;
-  const bool pair_ok = allow_pair && !p.compact && p.n_tiles % 2 == 0 && p.n_tok % 32 == 0 && sm_count >= 2;
+  const bool pair_ok = allow_pair && p.n_tiles % 2 == 0 && p.n_tok % 32 == 0 && sm_count >= 2;
   const bool pair_auto = p.n_tok == kMaxTok && p.m_tiles >= 2 && 2ll * p.m_tiles * p.n_tiles >= 5ll * sm_count;
   p.pair = (pair_ok && (env_pair == 1 || (env_pair != 0 && pair_auto))) ? 1 : 0;
   const int sched_cols = p.n_tiles >> p.pair;   // scheduled (super-)tiles per token tile
-  // CTAs (pairs) the schedule is distributed over; compact: two CTAs per SM
-  const int sched_ctas = p.compact ? 2 * sm_count : sm_count >> p.pair;
+  const int sched_ctas = sm_count >> p.pair;    // CTAs (pairs) the schedule is distributed over
   const long long tiles = (long long)p.m_tiles * sched_cols;
   const long long units = tiles * p.k_units;
   if (units >= (1ll << 31)) {
@@ -256,7 +247,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
   const int g_auto = p.n_tok <= 64 ? 3 : 2;
   (void)grouped;
-  p.unpack_groups = p.compact ? 1 : ((env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto);
+  p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
   // Weight-ring depth must be a multiple of `period`.  Sub-block i = ksub*unit + sub is unpacked by group i % G,
   // and a group only waits on the full-barrier of the stages it unpacks from.  mbarrier waits are by phase PARITY:
   // a group that waits for unit w on a stage whose previous occupant (unit w - depth) it never waited on can find
@@ -270,9 +261,9 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   // (long latency, ~160 KB in flight); with several token tiles they mostly hit L2 (~64 KB).  The token ring
   // (L2-resident data) takes the rest, at least 3 and at most 6 stages.
   const int stage_t = p.ksub * (p.n_tok >> p.pair) * 128, stage_w = p.ksub * (kStageB + kStageS);
-  const int budget = (p.compact ? kCompactSmemBytes : kMaxSmemBytes) - 1024 - epi_stage_bytes(p.compact) -
-                     8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
-  const int inflight = p.compact ? 81920 : 163840;  // bytes of weights (or tokens) in flight per CTA
+  const int budget =
+      kMaxSmemBytes - 1024 - kEpiStageBytes - 8 * (4 * kMaxStages + 2 * kMaxASlots + 4) - 16 - 4 * kMaxTok;
+  const int inflight = 163840;  // bytes of weights (or tokens) in flight per CTA
   const int max_w = kMaxStages / period * period;
   auto round_w = [&](int n) { n = n > max_w ? max_w : n; return n / period * period; };
   int nsw = 0, nst = 0;
@@ -316,10 +307,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     const long long c_ints = 64ll * max_par * N;              // capacity of C
     auto parts_max = [&](long long upc) { return (upc % p.k_units == 0) ? 1ll : (p.k_units - 1) / upc + 2; };
     // (1) cut only the remainder tiles, over all CTAs, ahead of the whole tiles (fix-up hidden behind the rest)
-    long long upc_rem = (rem * p.k_units + grid - 1) / grid;
-    // compact: twice as many CTAs would cut a remainder tile into twice as many slices; the finisher reads every other
-    // slice's partial tile, so at most 4-5 contributors per tile
-    if (p.compact && upc_rem < (p.k_units + 3) / 4) upc_rem = (p.k_units + 3) / 4;
+    const long long upc_rem = (rem * p.k_units + grid - 1) / grid;
     // (2) fallback when C is too small for that many contributors per tile: one contiguous stream-K range per CTA
     //     over ALL tiles (at most 2-3 contributors per tile, but the fix-up of a CTA's last tile is exposed)
     const long long upc_all = (units + grid - 1) / grid;
@@ -337,7 +325,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
       const double c_kb = p.m_tiles > 1 ? (p.pair ? 552.0 : kb_cycles(p.n_tok))
                                         : 4.0 * (p.n_tok / 2 > 48 ? p.n_tok / 2 : 48) + 48.0;
       const double t_u = p.ksub * (p.m_tiles == 1 && c_kb < 420.0 ? 420.0 : c_kb);
-      const int n_epi = (p.compact ? kWarpsCompact : kWarps) - kUnpackWarp0 - 4 * p.unpack_groups;
+      const int n_epi = kWarps - kUnpackWarp0 - 4 * p.unpack_groups;
       const double t_d = 730.0 * ((p.n_tok / 16 + n_epi / 4 - 1) / (n_epi / 4)) + 1400.0;
       const bool dbuf = p.n_tok <= kDbufMaxTok;  // double-buffered accumulators: only the last drain of a CTA is exposed
       const long long waves = (tiles + grid - 1) / grid;
@@ -389,7 +377,7 @@ int qqq_b200_plan(int prob_m, int prob_n, int prob_k, int groupsize, int sm_coun
   if (rc != QQQ_OK) return rc;
   const int v[20] = {grid,      p.n_tok,   p.m_tiles, p.n_tiles,  p.k_blocks, p.ksub,    p.k_units,      p.a_tiles,
                      p.a_units, p.a_upc,   p.b_tiles, p.b_tpc,    p.stages_w, p.stages_t, p.unpack_groups,
-                     (int)qqq::gemm_smem_bytes(p), p.pair, p.b_step, p.compact, 0};
+                     (int)qqq::gemm_smem_bytes(p), p.pair, p.b_step, 0, 0};
   for (int i = 0; i < 20; ++i) out[i] = v[i];
   return QQQ_OK;
 }
@@ -468,7 +456,7 @@ static int gemm_impl(const void* A, const void* B, void* C, void* D, const void*
   int grid = 0;
   {
     const int rc = plan_gemm(M, N, K, grouped, sm_count, max_par, C != nullptr && workspace != nullptr, p, &grid,
-                             /*allow_pair=*/out_mode == 0, /*allow_compact=*/out_mode != 2);
+                             /*allow_pair=*/out_mode == 0);
     if (rc != QQQ_OK) return rc;
   }
   p.out_mode = out_mode;

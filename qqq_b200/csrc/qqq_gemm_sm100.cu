@@ -191,13 +191,8 @@ __device__ __forceinline__ void emit_d(__half* dp, const uint4& v) {
 
 // kAcc (qqq_gemm_acc_sm100a): the finished tile leaves as the raw int32 accumulators, row-major [M, N] int32, no scales —
 // for the bit-exact tensor-parallel mode (int32 partial sums are all-reduced, the scales applied once afterwards).
-// kNW = warps per CTA: kWarps (20; one CTA per SM with the whole shared memory and all 512 TMEM columns), or kWarpsCompact
-// (12: one unpack group + 4 epilogue warps, half of the shared memory, 256 TMEM columns) for decode-size token tiles, so
-// that TWO CTAs fit an SM: with programmatic dependent launch the CTAs of the NEXT kernel in the stream move in while this
-// kernel's last CTAs are still draining and run their prologue, weight TMAs and unpack under that tail — at decode a GEMM
-// is a ~10 us kernel of which ~4 us were launch, prologue, first DRAM round trip and the last drain.
-template <bool GROUPED, bool kPair, int kOut = kOutStore, int kNW = kWarps>
-__global__ void __launch_bounds__(32 * kNW, kNW == kWarps ? 1 : 2)
+template <bool GROUPED, bool kPair, int kOut = kOutStore>
+__global__ void __launch_bounds__(kThreads, 1)
 qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
   constexpr bool kAcc = kOut == kOutAcc;
@@ -210,7 +205,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // one tile overlaps the MMAs of the next), then the ring of unpacked weight tiles (one slot = one unit = 32*KSUB columns)
   const int ndbuf = p.n_tok <= kDbufMaxTok ? 2 : 1;
   const int tmem_a0 = ndbuf * p.n_tok;
-  const int tmem_cols = kNW == kWarps ? 512 : 256;
+  constexpr int tmem_cols = 512;
   const int NA = min(kMaxASlots, (tmem_cols - tmem_a0) / (32 * KSUB));
   // CTA pair (cluster of 2, tcgen05 cta_group::2): the two CTAs take adjacent 128-channel tiles of the same token tile
   // and the same k-range; one MMA instruction of the leader (rank 0) drives both tensor cores (UMMA M = 256), every
@@ -221,7 +216,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int tok_bytes = tok_rows * 128;               // one sub-block of tokens in this CTA's shared memory
   const int stage_w = KSUB * kStageB, stage_t = KSUB * tok_bytes, stage_s = KSUB * kStageS;
   uint8_t* sStage = smem;                   // epilogue staging: one [16][32] fp16 tile per epilogue warp
-  uint8_t* sT = sStage + epi_stage_bytes(kNW != kWarps);
+  uint8_t* sT = sStage + kEpiStageBytes;
   uint8_t* sW = sT + NST * stage_t;
   uint8_t* sS = sW + NSW * stage_w;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sS + NSW * stage_s);
@@ -239,7 +234,7 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.unpack_groups;                 // 2 or 3 groups of unpack warps (host policy in qqq_c_api.cu)
   const int epi_warp0 = kUnpackWarp0 + 4 * G;    // warps [epi_warp0, kWarps) drain the accumulators
-  const int n_epi = kNW - epi_warp0;             // 8 or 4 epilogue warps
+  const int n_epi = kWarps - epi_warp0;          // 8 or 4 epilogue warps
   const int n_epi_thr = 32 * n_epi;
   const int KU = p.k_units;  // units per tile
   const Sched sched(p, (int)blockIdx.x >> PAIR);  // the schedule is over (super-)tiles: both CTAs of a pair walk it
@@ -733,45 +728,34 @@ qqq_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 }  // namespace
 
 size_t gemm_smem_bytes(const GemmParams& p) {
-  return 1024 + epi_stage_bytes(p.compact) + (size_t)p.stages_t * p.ksub * (p.n_tok >> p.pair) * 128 +
+  return 1024 + kEpiStageBytes + (size_t)p.stages_t * p.ksub * (p.n_tok >> p.pair) * 128 +
          (size_t)p.stages_w * p.ksub * (kStageB + kStageS) +
          8 * (2 * p.stages_w + 2 * p.stages_t + 2 * kMaxASlots + 4) + 16 + 4 * kMaxTok;
 }
 
 cudaError_t launch_gemm(const CUtensorMap& tmap_a, const CUtensorMap& tmap_b, const GemmParams& p, bool grouped,
                         int grid, int dev, cudaStream_t stream, bool pdl) {
-  static bool attr_set[16][64] = {};  // the opt-in shared-memory attribute is per device
+  static bool attr_set[10][64] = {};  // the opt-in shared-memory attribute is per device
   const size_t smem = gemm_smem_bytes(p);
   if (p.out_mode != kOutStore && p.pair) return cudaErrorInvalidValue;  // the planner never pairs these launches
   if (p.out_mode < 0 || p.out_mode > kOutScatter) return cudaErrorInvalidValue;
-  if (p.compact && (p.pair || p.out_mode == kOutAcc)) return cudaErrorInvalidValue;
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const GemmParams);
-  constexpr int C = kWarpsCompact;
-  static const Kern table[16] = {
+  static const Kern table[10] = {
       qqq_gemm_kernel<false, false>, qqq_gemm_kernel<true, false>, qqq_gemm_kernel<false, true>, qqq_gemm_kernel<true, true>,
       qqq_gemm_kernel<false, false, kOutReduce>, qqq_gemm_kernel<true, false, kOutReduce>,
       qqq_gemm_kernel<false, false, kOutAcc>, qqq_gemm_kernel<true, false, kOutAcc>,
-      qqq_gemm_kernel<false, false, kOutScatter>, qqq_gemm_kernel<true, false, kOutScatter>,
-      qqq_gemm_kernel<false, false, kOutStore, C>, qqq_gemm_kernel<true, false, kOutStore, C>,
-      qqq_gemm_kernel<false, false, kOutReduce, C>, qqq_gemm_kernel<true, false, kOutReduce, C>,
-      qqq_gemm_kernel<false, false, kOutScatter, C>, qqq_gemm_kernel<true, false, kOutScatter, C>};
+      qqq_gemm_kernel<false, false, kOutScatter>, qqq_gemm_kernel<true, false, kOutScatter>};
   const int g1 = grouped ? 1 : 0;
-  const int variant = p.compact ? (p.out_mode == kOutStore ? 10 : p.out_mode == kOutReduce ? 12 : 14) + g1
-                      : p.out_mode != kOutStore ? 2 + 2 * p.out_mode + g1
-                                                : g1 + (p.pair ? 2 : 0);
+  const int variant = p.out_mode != kOutStore ? 2 + 2 * p.out_mode + g1 : g1 + (p.pair ? 2 : 0);
   const Kern kern = table[variant];
   if (dev < 0 || dev >= 64 || !attr_set[variant][dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         p.compact ? kCompactSmemBytes : kMaxSmemBytes);
-    if (e != cudaSuccess) return e;
-    // the whole L1/shared array as shared memory: the compact variant needs it for two CTAs per SM
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemBytes);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[variant][dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(32 * (p.compact ? kWarpsCompact : kWarps));
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

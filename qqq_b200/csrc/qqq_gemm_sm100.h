@@ -24,8 +24,7 @@ constexpr int kMaxTok = 256;     // token tile (UMMA N) upper bound
 constexpr int kDbufMaxTok = QQQ_DBUF_MAX_TOK;
 constexpr int kMaxSmemBytes = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr int kStageD = 1024;          // one epilogue staging tile: 16 tokens x 32 channels fp16 (one warp's chunk)
-constexpr int kEpiStageBytes = 8 * kStageD;  // up to 8 epilogue warps (compact variant: 4)
-__host__ __device__ constexpr int epi_stage_bytes(bool compact) { return compact ? 4 * kStageD : kEpiStageBytes; }
+constexpr int kEpiStageBytes = 8 * kStageD;  // up to 8 epilogue warps
 // warp roles: 0 weights TMA, 1 MMA (+TMEM alloc), 2 tokens TMA, 3 idle, then 4*G unpack warps (G groups x 4 TMEM
 // lane quadrants) and the remaining 16-4G warps as epilogue (G = 2: 8 epilogue warps, G = 3: 4).  24 warps
 // (G up to 4) were measured and did not help: all warps of a TMEM quadrant share one SM sub-partition, so extra
@@ -33,10 +32,6 @@ __host__ __device__ constexpr int epi_stage_bytes(bool compact) { return compact
 constexpr int kUnpackWarp0 = 4;
 constexpr int kWarps = 20;
 constexpr int kThreads = 32 * kWarps;
-// compact variant (decode-size token tiles): W, MMA, T, idle + ONE unpack group + 4 epilogue warps; two such CTAs share an
-// SM (half of the shared memory and 256 of the 512 TMEM columns each)
-constexpr int kWarpsCompact = 12;
-constexpr int kCompactSmemBytes = 113 * 1024;  // two CTAs + 1 KB of system reservation each fit the SM's 228 KB
 
 struct GemmParams {
   int32_t* C;        // split-K scratch: compact [n_tok][128] int32 partial tiles, block = ticket * tiles + tile
@@ -53,7 +48,6 @@ struct GemmParams {
   int k_units;       // ceil(k_blocks / ksub): pipeline stages ("units") per tile
   int stages_w, stages_t;  // depth of the weight / token smem rings
   int unpack_groups;       // 2 or 3 groups of 4 unpack warps; the other 16-4G non-control warps are epilogue warps
-  int compact;             // 1: compact variant (kWarpsCompact warps, two CTAs per SM, 256 TMEM columns); never with pair
   int pair;                // 1: CTA pairs (cluster of 2, cta_group::2): scheduled tiles are 256 channels wide, each CTA of
                            // a pair owns 128 of them and loads half of the token tile; n_tiles stays in 128-channel tiles
   // two-phase schedule (see Sched in qqq_gemm_sm100.cu); a unit = (tile, k-unit), tile = mt + m_tiles*nt

@@ -33,7 +33,8 @@
 
 namespace qqq {
 
-constexpr int kTpThreads = 256;
+constexpr int kTpThreads = 256;     // threads per token row
+constexpr int kTpRowsPerCta = 2;    // rows a CTA works on at a time
 constexpr int kTpMaxWorld = 8;
 constexpr unsigned long long kSpinTimeoutNs = 2000000000ull;  // 2 s
 
@@ -120,24 +121,28 @@ __device__ __forceinline__ uint4 sum_chunk(const uint4* __restrict__ part, size_
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// One WARP per owned token row (8 rows in flight per CTA, rows strided over all warps of the grid): a row needs no CTA-wide
-// barrier, so its latency is two sweeps of loads (pass 1: sum + row maximum; pass 2: the sums again — L2 hits — quantised
-// and sent out) instead of load -> barrier -> barrier -> store per row and CTA.  A lane owns units of 16 consecutive
-// channels (two 16-byte chunks of fp16 in, ONE 16-byte piece of int8 out: NVLink moves 16-byte multicast stores at several
-// times the rate of 8-byte ones).
-__global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpReduceParams p) {
+// kTpRowsPerCta token rows at a time per CTA (one group of kTpThreads threads per row, rows strided over the groups of the
+// grid): system-scope fences are the expensive part of this kernel and there is one per CTA, so few, fat CTAs.  A thread owns NCH units of 16 consecutive channels (two 16-byte chunks of
+// fp16 in, ONE 16-byte piece of int8 out: NVLink moves 16-byte multicast stores at several times the rate of 8-byte
+// ones); the units stay in registers between the reduction / max pass and the quantise pass (NCH == 0: any N, the second
+// pass recomputes the sum).
+template <int NCH>
+__global__ void __launch_bounds__(kTpThreads * kTpRowsPerCta) tp_reduce_quant_kernel(const TpReduceParams p) {
   grid_launch_dependents();  // the next GEMM may run its prologue and prefetch its weights under this kernel
   grid_dependency_wait();    // the row-shard GEMM of this rank has completed: its peer stores are performed
   __shared__ uint32_t sh_epoch;
   __shared__ uint32_t sh_last;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) sh_epoch = *reinterpret_cast<volatile uint32_t*>(p.flags + 16) + 1u;
+  __shared__ __half red_all[kTpRowsPerCta][kTpThreads / 32];
+  const int group = threadIdx.x / kTpThreads;  // which of the CTA's concurrent rows this thread works on
+  __half* red = red_all[group];
+  const int tid = threadIdx.x % kTpThreads;    // position inside the row group
+  if (threadIdx.x == 0) sh_epoch = *reinterpret_cast<volatile uint32_t*>(p.flags + 16) + 1u;
   __syncthreads();
   const uint32_t epoch = sh_epoch;
   // arrive-1: "my GEMM's rows are in your slots" to every rank (one CTA sends), then every CTA waits for all senders
-  if (blockIdx.x == 0 && tid < p.world) st_release_sys(p.peer_flags[tid] + p.rank, epoch);
-  if (tid < p.world) {
-    if (!wait_epoch(p.flags + tid, epoch)) atomicAdd(p.flags + 18, 1u);
+  if (blockIdx.x == 0 && threadIdx.x < p.world) st_release_sys(p.peer_flags[threadIdx.x] + p.rank, epoch);
+  if (threadIdx.x < p.world) {
+    if (!wait_epoch(p.flags + threadIdx.x, epoch)) atomicAdd(p.flags + 18, 1u);
   }
   __syncthreads();
 
@@ -147,25 +152,48 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpRed
   const size_t slot_stride16 = (size_t)p.rows_cap * N8;
   const uint4* part16 = reinterpret_cast<const uint4*>(p.part);
   const uint4* bias16 = reinterpret_cast<const uint4*>(p.bias);
-  constexpr int kWarpsPerCta = kTpThreads / 32;
-  for (int row = blockIdx.x * kWarpsPerCta + warp; row < my_rows; row += gridDim.x * kWarpsPerCta) {
+  constexpr int NC = NCH > 0 ? NCH : 1;
+  for (int row = blockIdx.x * kTpRowsPerCta + group; row < my_rows; row += gridDim.x * kTpRowsPerCta) {
     const size_t row16 = (size_t)row * N8;
     const size_t grow = (size_t)p.rank * p.rows_cap + row;  // row of the gathered buffers
+    uint4 cache[2 * NC];
     uint32_t m = 0;
-    for (int u = lane; u < N16; u += 32) {
-      const uint4 a = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u, bias16, 2 * u);
-      const uint4 b = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u + 1, bias16, 2 * u + 1);
+    auto load_unit = [&](int u, uint4& a, uint4& b) {
+      a = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u, bias16, 2 * u);
+      b = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u + 1, bias16, 2 * u + 1);
       m = hmax2_u32(hmax2_u32(m, habs2_u32(a.x)), habs2_u32(a.y));
       m = hmax2_u32(hmax2_u32(m, habs2_u32(a.z)), habs2_u32(a.w));
       m = hmax2_u32(hmax2_u32(m, habs2_u32(b.x)), habs2_u32(b.y));
       m = hmax2_u32(hmax2_u32(m, habs2_u32(b.z)), habs2_u32(b.w));
+    };
+    if (NCH > 0) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int u = tid + j * kTpThreads;
+        if (u < N16) {
+          load_unit(u, cache[2 * j], cache[2 * j + 1]);
+        } else {
+          cache[2 * j] = cache[2 * j + 1] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    } else {
+      for (int u = tid; u < N16; u += kTpThreads) {
+        uint4 a, b;
+        load_unit(u, a, b);
+      }
     }
     __half2 mh = *reinterpret_cast<__half2*>(&m);
     __half mx = __hmax_nan(__low2half(mh), __high2half(mh));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = __hmax_nan(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float s = token_scale(mx);
-    if (lane == 0) {
+    named_bar_sync(1 + group, kTpThreads);  // `red` of the previous row has been read by everybody in the row group
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    named_bar_sync(1 + group, kTpThreads);
+    __half t = red[0];
+#pragma unroll
+    for (int i = 1; i < kTpThreads / 32; ++i) t = __hmax_nan(t, red[i]);
+    const float s = token_scale(t);
+    if (tid == 0) {
       if (p.s1_mc != nullptr) {
         multimem_st_4(p.s1_mc + grow, __float_as_uint(s));
       } else {
@@ -174,9 +202,7 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpRed
     }
     const bool fast = s > 0.f && s < __int_as_float(0x7F800000);
     const float rcp = __frcp_rn(s);
-    for (int u = lane; u < N16; u += 32) {
-      const uint4 a = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u, bias16, 2 * u);
-      const uint4 b = sum_chunk(part16, slot_stride16, p.world, row16 + 2 * u + 1, bias16, 2 * u + 1);
+    auto emit = [&](int u, const uint4& a, const uint4& b) {
       const uint4 q = fast ? make_uint4(quant4<true>(a.x, a.y, s, rcp), quant4<true>(a.z, a.w, s, rcp),
                                         quant4<true>(b.x, b.y, s, rcp), quant4<true>(b.z, b.w, s, rcp))
                            : make_uint4(quant4<false>(a.x, a.y, s, rcp), quant4<false>(a.z, a.w, s, rcp),
@@ -191,6 +217,21 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpRed
         reinterpret_cast<uint4*>(p.h_out)[row16 + 2 * u] = a;
         reinterpret_cast<uint4*>(p.h_out)[row16 + 2 * u + 1] = b;
       }
+    };
+    if (NCH > 0) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int u = tid + j * kTpThreads;
+        if (u < N16) emit(u, cache[2 * j], cache[2 * j + 1]);
+      }
+    } else {
+      for (int u = tid; u < N16; u += kTpThreads) {
+        uint4 a, b;
+        uint32_t keep = m;
+        load_unit(u, a, b);
+        m = keep;
+        emit(u, a, b);
+      }
     }
   }
 
@@ -201,35 +242,36 @@ __global__ void __launch_bounds__(kTpThreads) tp_reduce_quant_kernel(const TpRed
   // finished-CTA counter; whoever sees the counter complete therefore knows that every CTA's rows have been performed
   // at system scope and can raise the flags with plain system-scope stores.
   __syncthreads();
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     __threadfence_system();
     const uint32_t done = atomicAdd(p.flags + 17, 1u);
     sh_last = (done == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
   if (sh_last) {
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
       p.flags[17] = 0;
       p.flags[16] = epoch;
     }
-    if (tid < p.world) {
-      st_relaxed_sys(p.peer_flags[tid] + 8 + p.rank, epoch);
-      if (!wait_epoch(p.flags + 8 + tid, epoch)) atomicAdd(p.flags + 18, 1u);
+    if (threadIdx.x < p.world) {
+      st_relaxed_sys(p.peer_flags[threadIdx.x] + 8 + p.rank, epoch);
+      if (!wait_epoch(p.flags + 8 + threadIdx.x, epoch)) atomicAdd(p.flags + 18, 1u);
     }
   }
 }
 
+template <int NCH>
 static cudaError_t launch_tp(const TpReduceParams& p, int grid, cudaStream_t stream, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kTpThreads);
+  cfg.blockDim = dim3(kTpThreads * kTpRowsPerCta);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tp_reduce_quant_kernel, p);
+  return cudaLaunchKernelEx(&cfg, tp_reduce_quant_kernel<NCH>, p);
 }
 
 cudaError_t launch_tp_reduce_quant(const void* part, void* const* a8_dst, void* a8_mc, void* const* s1_dst, void* s1_mc,
@@ -252,11 +294,16 @@ cudaError_t launch_tp_reduce_quant(const void* part, void* const* a8_dst, void* 
   p.rows_cap = rows_cap;
   p.M = M;
   p.N = N;
+  // one CTA per SM measured best (fewer fences and counter bumps; rows are grid-strided); QQQ_B200_TPGRID overrides
+  static const int env_grid = getenv("QQQ_B200_TPGRID") ? atoi(getenv("QQQ_B200_TPGRID")) : 148;
   const int my_rows = M - rank * rows_cap < 0 ? 0 : (M - rank * rows_cap < rows_cap ? M - rank * rows_cap : rows_cap);
-  // one warp per row, 8 warps per CTA; every rank launches at least one CTA: it still takes part in both flag exchanges
-  const int want = (my_rows + kTpThreads / 32 - 1) / (kTpThreads / 32);
-  const int grid = want < 1 ? 1 : (want > 592 ? 592 : want);
-  return launch_tp(p, grid, stream, pdl);
+  // every rank launches at least one CTA: it still takes part in both flag exchanges
+  const int want = (my_rows + kTpRowsPerCta - 1) / kTpRowsPerCta;
+  const int grid = want < 1 ? 1 : (want > env_grid ? env_grid : want);
+  const int nch = (N / 16 + kTpThreads - 1) / kTpThreads;  // 16-channel units per thread
+  if (nch <= 1) return launch_tp<1>(p, grid, stream, pdl);
+  if (nch <= 2) return launch_tp<2>(p, grid, stream, pdl);
+  return launch_tp<0>(p, grid, stream, pdl);
 }
 
 }  // namespace qqq

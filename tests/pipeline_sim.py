@@ -83,10 +83,9 @@ class CtaSim:
         self.NSW, self.NST = plan["stages_w"], plan["stages_t"]
         self.n_tok, self.M, self.m_tiles = plan["n_tok"], M, plan["m_tiles"]
         self.ndbuf = 2 if self.n_tok <= dbuf_max_tok else 1
-        self.compact = plan.get("compact", 0)  # 12-warp CTA with 256 TMEM columns (two CTAs per SM)
-        self.NA = min(K_MAX_A_SLOTS, ((256 if self.compact else 512) - self.ndbuf * self.n_tok) // (32 * self.KSUB))
+        self.NA = min(K_MAX_A_SLOTS, (512 - self.ndbuf * self.n_tok) // (32 * self.KSUB))
         assert self.NA >= 1, "no room for the TMEM weight ring"
-        self.n_epi = (12 if self.compact else K_WARPS) - K_UNPACK_WARP0 - 4 * self.G
+        self.n_epi = K_WARPS - K_UNPACK_WARP0 - 4 * self.G
         self.pair = 2 if twin else 1  # arrival multiplier on the leader's shared barriers
         mk = lambda name, n, cnt: [MBar(f"{name}[{i}]", cnt) for i in range(n)]  # noqa: E731
         self.fullw, self.emptyw = mk("fullw", self.NSW, 1), mk("emptyw", self.NSW, 4 * self.KSUB)

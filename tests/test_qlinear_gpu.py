@@ -46,7 +46,7 @@ def test_forward_keeps_leading_dims_and_bias():
                                       (32, 4096, 4096, 128), (2, 256, 64, -1)])
 def test_bias_in_the_epilogue_equals_the_reference_two_step_result(M, K, N, gs):
     """`D + bias` (qlinear_marlin.py:286-288) folded into the GEMM epilogue: identical bits to the oracle's D followed by an
-    fp16 add, over whole-tile, stream-K (finisher) and compact-variant schedules, ragged M and N % 128 == 64."""
+    fp16 add, over whole-tile and stream-K (finisher) schedules, ragged M and N % 128 == 64."""
     p = O.make_problem(M, K, N, gs, seed=M + N)
     ql = _module(p, K, N, gs)
     bias = torch.randn(N, generator=torch.Generator().manual_seed(N)).half()

@@ -10,7 +10,7 @@ import pytest
 from qqq_b200 import _lib
 
 KEYS = ["grid", "n_tok", "m_tiles", "n_tiles", "k_blocks", "ksub", "k_units", "a_tiles", "a_units", "a_upc", "b_tiles",
-        "b_tpc", "stages_w", "stages_t", "unpack_groups", "smem_bytes", "pair", "b_step", "compact", "_r3"]
+        "b_tpc", "stages_w", "stages_t", "unpack_groups", "smem_bytes", "pair", "b_step", "_r2", "_r3"]
 
 
 def plan(M, N, K, gs=-1, sms=148, max_par=16):
@@ -57,17 +57,15 @@ def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
     assert pair in (0, 1) and (pair == 0 or (p["n_tiles"] % 2 == 0 and p["n_tok"] % 32 == 0 and p["grid"] % 2 == 0))
     KU, tiles = p["k_units"], p["m_tiles"] * (p["n_tiles"] >> pair)
     assert p["a_tiles"] + p["b_tiles"] == tiles and p["a_units"] == p["a_tiles"] * KU
-    compact = p["compact"]  # decode-size tiles: 12-warp CTAs, two per SM (half the shared memory, 256 TMEM columns each)
-    assert compact in (0, 1) and (compact == 0 or (pair == 0 and p["n_tok"] <= 64 and p["m_tiles"] == 1))
-    assert 1 <= p["grid"] <= sms * (2 if compact else 1)
+    assert 1 <= p["grid"] <= sms
     p = dict(p, grid=p["grid"] >> pair)  # schedule indices
     assert p["n_tok"] % 16 == 0 and 16 <= p["n_tok"] <= 256 and p["m_tiles"] * p["n_tok"] >= M
     assert p["ksub"] in (1, 2, 4) and KU == -(-p["k_blocks"] // p["ksub"])
-    assert p["smem_bytes"] <= (113 * 1024 if compact else 232448) and p["stages_w"] >= 2 and p["stages_t"] >= 2
-    assert p["unpack_groups"] in ((1,) if compact else (2, 3))
+    assert p["smem_bytes"] <= 232448 and p["stages_w"] >= 2 and p["stages_t"] >= 2
+    assert p["unpack_groups"] in (2, 3)
     # TMEM: two accumulators (n_tok <= 208) or one, plus at least two slots of 32*ksub columns for the unpacked weights
     acc_cols = (2 if p["n_tok"] <= 208 else 1) * p["n_tok"]
-    assert ((256 if compact else 512) - acc_cols) // (32 * p["ksub"]) >= 2
+    assert (512 - acc_cols) // (32 * p["ksub"]) >= 2
     # a weight stage must always be consumed by the same unpack groups (mbarrier waits are by phase parity):
     # sub-block i = ksub*unit + sub belongs to group i % G, so the ring depth has to be a multiple of the period of
     # that ownership pattern in units
@@ -103,16 +101,10 @@ def test_every_unit_covered_exactly_once(M, N, K, sms, gs):
         assert (tiles << pair) <= (N // 128) * 16, "not enough lock words in workspace"
 
 
-def test_decode_plans_use_the_compact_variant():
-    """Decode-size token tiles run as compact CTAs (two per SM, so the next kernel's CTAs can move in under this kernel's
-    tail): at most 2 x SMs CTAs, and a remainder tile is never cut into more than five slices (the finisher reads every
-    other slice's partial tile)."""
-    for (M, N, K, gs) in [(16, 21760, 8192, -1), (32, 4096, 4096, 128), (32, 1024, 4096, 128), (32, 28672, 4096, 128),
-                          (32, 4096, 14336, 128), (64, 21760, 8192, -1), (1, 4096, 4096, -1)]:
-        p = plan(M, N, K, gs)
-        assert p["compact"] == 1 and p["pair"] == 0 and p["unpack_groups"] == 1 and p["grid"] <= 2 * 148
-        KU = p["k_units"]
-        for t in range(p["a_tiles"]):
-            parts = (t * KU + KU - 1) // p["a_upc"] - (t * KU) // p["a_upc"] + 1
-            assert parts <= 5 or p["a_upc"] * 296 >= p["a_units"], (M, N, K, parts)
-    assert plan(128, 21760, 8192)["compact"] == 0 and plan(1024, 4096, 4096)["compact"] == 0
+def test_decode_plan_hides_the_fixup():
+    """At decode the split remainder tiles are processed first and every CTA ends on a whole tile."""
+    p = plan(16, 21760, 8192)
+    assert p["a_tiles"] == 170 - 148 and p["b_tpc"] == 1 and p["grid"] == 148
+    for cta in range(p["grid"]):
+        segs = segments(p, cta)
+        assert segs[-1][1:] == (0, p["k_units"])
