@@ -313,7 +313,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     const long long upc_all = (units + grid - 1) / grid;
     // (1) multiplies the contributors per tile (and with them the partial-tile traffic of the fix-up), so it is
     // used for decode-size tiles only; measured: wins at n_tok <= 32, loses from 64 tokens up.
-    if (p.n_tok <= 32 && (parts_max(upc_rem) - 1) * rem * tile_ints <= c_ints) {
+    if ((p.n_tok <= 32 || env_split == 2) && (parts_max(upc_rem) - 1) * rem * tile_ints <= c_ints) {
       a_tiles = rem;
       a_upc = upc_rem;
     } else if ((parts_max(upc_all) - 1) * tiles * tile_ints <= c_ints) {
