@@ -183,7 +183,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     return n <= 128 ? 350.0 + 0.94 * n : (n <= 208 ? 470.0 + 1.625 * (n - 128) : 590.0);
   };
   p.n_tok = tile_tokens(kMaxTok, &p.m_tiles);
-  if (M > kMaxTok) {
+  if (M > 128) {
     // ... unless smaller tiles fill the SMs so much better that they win despite their higher cost per token.
     // Cost model from the round-2 measurements (profiles/r02/call_b, call_f): a 128-deep k-block of a tile costs
     // ~350 + 0.94 * n_tok cycles up to 128 tokens, ~600 at 208 and ~590 at 256 (operand traffic L2 -> SM and hand-offs, not
@@ -332,12 +332,13 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
       const double t_dw = t_d;
       const double cost_whole = (double)waves * p.k_units * t_u + (dbuf ? 1.0 : (double)waves) * t_dw;
       const long long segs = (upc_all + p.k_units - 1) / p.k_units + 1;
-      // a CTA of a stream-K schedule publishes one partial tile and finishes another: int32 partials (2x the bytes of the
-      // fp16 output) go through L2 both ways and the finisher waits for its contributors — measured ~30 cycles per token
-      // and straddled tile on top of the plain drain (profiles/r02/call_b: stream-K lost 7 % at (1024, 4096, 11008) and
-      // (1024, 8192, 21760) where the older model, without this term, chose it)
-      const double t_fix = 30.0 * p.n_tok + 500.0;
-      const double cost_split = (double)upc_all * t_u + (dbuf ? 1.0 : (double)segs) * t_d + 2.0 * t_fix;
+      // A CTA of a stream-K schedule publishes one partial tile and finishes another: int32 partials (2x the bytes of the
+      // fp16 output) go through L2 both ways, the publisher's fence + announcement costs ~5 k cycles after its drain and
+      // the finisher can only start when the slowest contributor has announced.  Measured end to end (profiles/r02/call_m):
+      // ~10 k cycles + 40 per token on top of the plain drain — (128, 4096, 4096) took 23.0 us as stream-K over 148 CTAs
+      // against 10.7 us as 32 whole tiles, while (128, 8192, 21760) wins 29.0 vs 33.3 us because it saves 54 k-blocks per CTA.
+      const double t_fix = 10000.0 + 40.0 * p.n_tok;
+      const double cost_split = (double)upc_all * t_u + (dbuf ? 1.0 : (double)segs) * t_d + t_fix;
       if (env_split == 1 || cost_split < cost_whole) {
         a_tiles = tiles;
         a_upc = upc_all;

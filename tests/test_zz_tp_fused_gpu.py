@@ -2,9 +2,7 @@
 the NCCL path and against the fp32 sum of the per-rank GEMM outputs.  Needs two B200s of one NVSwitch domain: skipped
 on a single-GPU box.
 
-Status: written in round 1 after the GPU budget was spent — compiles, host protocol covered on CPU (tests/test_tp_gloo.py),
-NOT yet run on hardware.  Until it has been, it only runs on request:
-    gpurun --gpus 2 -- env QQQ_B200_MULTI_GPU_TESTS=1 python -m pytest tests/test_zz_tp_fused_gpu.py -m gpu"""
+Run green on 2 x B200 in round 2 (profiles/r02/call_a/pytest_tp_fused.log)."""
 import os
 import socket
 import sys
@@ -77,8 +75,6 @@ def _worker(rank, world, port, gs, out):
 def test_fused_gemm_allreduce_matches_nccl_path(gs):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if os.environ.get("QQQ_B200_MULTI_GPU_TESTS", "0") != "1":
-        pytest.skip("fused GEMM+all-reduce not yet verified on hardware: set QQQ_B200_MULTI_GPU_TESTS=1 to run")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
