@@ -879,7 +879,36 @@ def main():
         h = graphed(x_host)  # pinned host -> static device input (H2D), graph replay
         out_host.copy_(h, non_blocking=True)  # D2H of the step's result (N > 1: this rank's rows / replica)
 
-    ms_e2e = max_over_ranks(timed(e2e_step, args.steps, args.warmup, barrier))
+    ms_e2e_serial = max_over_ranks(timed(e2e_step, args.steps, args.warmup, barrier))
+    # ... and software-pipelined over two graphs (qqq_b200.graph.PipelinedRunner): the H2D copy of step i+1 and the D2H copy
+    # of step i-1 run on their own streams under the kernels of step i; every step still copies its input and its result
+    qqq_b200.set_act_quant_cache(True)
+    runner = qgraph.PipelinedRunner(chain, x_dev)
+    qqq_b200.set_act_quant_cache(False)
+    outs_host = [out_host, torch.empty_like(out_host).pin_memory()]
+
+    def e2e_pipelined():
+        runner.step(x_host, outs_host[runner.i & 1])
+
+    def timed_pipelined():
+        for _ in range(max(args.warmup, 2)):
+            e2e_pipelined()
+        runner.drain()
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_pipelined()
+        runner.drain()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        return e0.elapsed_time(e1) / args.steps
+
+    ms_e2e = max_over_ranks(timed_pipelined())
+    e2e_same = bool(torch.equal(outs_host[0], outs_host[1]))  # both graphs, same input: same result on the host
+    del runner
 
     # the same step through the eager public API (no graph), for the record
     def eager_step():
@@ -944,8 +973,10 @@ def main():
                 clocks=cs.summary(),
                 e2e=dict(value=round(M / (ms_e2e * 1e-3), 1), unit="tokens/s", ms_per_step=round(ms_e2e, 4),
                          h2d_bytes_per_step=x_host.numel() * 2, d2h_bytes_per_step=out_host.numel() * 2,
-                         api="qqq_b200.graph.capture(QuantLinear chain); eager QuantLinear.forward loop: "
-                             f"{ms_eager:.3f} ms/step"),
+                         api="qqq_b200.graph.PipelinedRunner(QuantLinear chain): two captured graphs, copies of neighbouring "
+                             f"steps overlap the kernels; one graph, copies in line: {ms_e2e_serial:.3f} ms/step; eager "
+                             f"QuantLinear.forward loop: {ms_eager:.3f} ms/step",
+                         results_identical_across_graphs=e2e_same),
                 gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
                 launch_mode="cuda-graph replay of the per-step launches" + (
                     "; q/k/v and gate/up are parallel branches of the graph (forked streams)" if OVERLAP else ""),

@@ -183,7 +183,7 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     return n <= 128 ? 350.0 + 0.94 * n : (n <= 208 ? 470.0 + 1.625 * (n - 128) : 590.0);
   };
   p.n_tok = tile_tokens(kMaxTok, &p.m_tiles);
-  if (M > 128) {
+  if (M > 64) {
     // ... unless smaller tiles fill the SMs so much better that they win despite their higher cost per token.
     // Cost model from the round-2 measurements (profiles/r02/call_b, call_f): a 128-deep k-block of a tile costs
     // ~350 + 0.94 * n_tok cycles up to 128 tokens, ~600 at 208 and ~590 at 256 (operand traffic L2 -> SM and hand-offs, not
@@ -192,8 +192,8 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     // Whole-tile waves are compared; stream-K (below) only smooths the remainder.  208 tokens = the largest tile that
     // still leaves room for two accumulators and a 3-slot weight ring in TMEM (5 x 208 covers M = 1024).
     double best = 0.0;
-    const int caps[3] = {kMaxTok, kDbufMaxTok, 128};
-    for (int ci = 0; ci < 3; ++ci) {
+    const int caps[4] = {kMaxTok, kDbufMaxTok, 128, 64};
+    for (int ci = 0; ci < 4; ++ci) {
       int mt = 0;
       const int nt = tile_tokens(caps[ci], &mt);
       // 256-token tiles run as CTA pairs where the policy below turns pairs on (same rule): cheaper k-blocks, waves of pairs
@@ -246,7 +246,6 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
   // rate of the sub-partition, which a third warp on the same sub-partition cannot widen).
   static const int env_grp = getenv("QQQ_B200_GROUPS") ? atoi(getenv("QQQ_B200_GROUPS")) : 0;
   const int g_auto = p.n_tok <= 64 ? 3 : 2;
-  (void)grouped;
   p.unpack_groups = (env_grp >= 2 && env_grp <= 3) ? env_grp : g_auto;
   // Weight-ring depth must be a multiple of `period`.  Sub-block i = ksub*unit + sub is unpacked by group i % G,
   // and a group only waits on the full-barrier of the stages it unpacks from.  mbarrier waits are by phase PARITY:
@@ -311,33 +310,48 @@ int plan_gemm(int M, int N, int K, bool grouped, int sm_count, int max_par, bool
     // (2) fallback when C is too small for that many contributors per tile: one contiguous stream-K range per CTA
     //     over ALL tiles (at most 2-3 contributors per tile, but the fix-up of a CTA's last tile is exposed)
     const long long upc_all = (units + grid - 1) / grid;
+    // Cycle model from the in-kernel timelines (profiles/): a k-block of a single token tile costs 4 MMAs of
+    // max(48 issue, n_tok/2 pipe) cycles + ~48 of hand-off and not less than ~420 when the weights stream from DRAM; with
+    // several token tiles the measured kb_cycles(); a drain costs ~730 cycles per 16-token chunk and epilogue warp + ~1400.
+    // One token tile (decode, M <= 256): the weights stream from DRAM, 8 KB per k-block and CTA against 3334 B/clk of HBM
+    // for the whole chip (x1.15 measured) — 419 cycles with 148 CTAs streaming, but only the unpack floor (~300 per-group,
+    // ~200 per-channel) when a few CTAs have the memory system to themselves: (32, 4096, 1024) runs 32 k-blocks per CTA on
+    // 8 CTAs in 9.0 us, faster than 64 CTAs with 4 k-blocks each and a fix-up (16.2 us).
+    auto kb_single = [&](long long active) {
+      const double base = 4.0 * (p.n_tok / 2 > 48 ? p.n_tok / 2 : 48) + 48.0;
+      const double unpack = grouped ? 300.0 : 200.0, hbm = 2.83 * (double)active;
+      return base > unpack ? (base > hbm ? base : hbm) : (unpack > hbm ? unpack : hbm);
+    };
+    const long long active_whole = tiles < grid ? tiles : grid;
+    const double c_kb_multi = p.pair ? 552.0 : kb_cycles(p.n_tok);
+    const double t_u = p.ksub * (p.m_tiles > 1 ? c_kb_multi : kb_single(grid));              // all CTAs busy (split)
+    const double t_u_whole = p.ksub * (p.m_tiles > 1 ? c_kb_multi : kb_single(active_whole));  // one CTA per whole tile
+    const int n_epi = kWarps - kUnpackWarp0 - 4 * p.unpack_groups;
+    const double t_d = 730.0 * ((p.n_tok / 16 + n_epi / 4 - 1) / (n_epi / 4)) + 1400.0;
+    // A CTA that ends on a cut tile publishes a partial tile or finishes one: int32 partials (2x the bytes of the fp16
+    // output) go through L2 both ways, the publisher's fence + announcement costs ~5 k cycles after its drain and the
+    // finisher can only start when the slowest contributor has announced.  Measured end to end (profiles/r02/call_m,
+    // call_n): ~10 k cycles + 40 per token on top of the plain drain — (128, 4096, 4096) took 23.0 us as stream-K over 148
+    // CTAs against 10.7 us as 32 whole tiles, (32, 4096, 1024) 16.2 against 9.0 us, while (128, 8192, 21760) wins 29.0 vs
+    // 33.3 us and (32, 14336, 4096) 18.2 vs 31.8 us because they save dozens of k-blocks per CTA.
+    const double t_fix = 10000.0 + 40.0 * p.n_tok;
     // (1) multiplies the contributors per tile (and with them the partial-tile traffic of the fix-up), so it is
     // used for decode-size tiles only; measured: wins at n_tok <= 32, loses from 64 tokens up.
     if ((p.n_tok <= 32 || env_split == 2) && (parts_max(upc_rem) - 1) * rem * tile_ints <= c_ints) {
-      a_tiles = rem;
-      a_upc = upc_rem;
+      // with whole tiles behind the slices the fix-up is hidden; with fewer tiles than CTAs it is the CTA's tail
+      const double cost_whole = (double)p.k_units * t_u_whole + t_d;
+      const double cost_split = (double)upc_rem * t_u + t_d + t_fix;
+      if (whole_per_cta > 0 || env_split == 1 || env_split == 2 || cost_split < cost_whole) {
+        a_tiles = rem;
+        a_upc = upc_rem;
+      }
     } else if ((parts_max(upc_all) - 1) * tiles * tile_ints <= c_ints) {
       // Stream-K over all tiles balances the SMs but costs every CTA one more accumulator drain (its partial of a
-      // straddled tile), which is exposed when the accumulator is single-buffered.  Cycle model from the in-kernel
-      // timelines (profiles/): a k-block costs 4 MMAs of max(48 issue, n_tok/2 pipe) cycles + ~48 of hand-off, and
-      // not less than ~420 when the weights stream from DRAM (one token tile); a drain costs ~730 cycles per
-      // 16-token chunk and epilogue warp + ~1400 fixed.
-      const double c_kb = p.m_tiles > 1 ? (p.pair ? 552.0 : kb_cycles(p.n_tok))
-                                        : 4.0 * (p.n_tok / 2 > 48 ? p.n_tok / 2 : 48) + 48.0;
-      const double t_u = p.ksub * (p.m_tiles == 1 && c_kb < 420.0 ? 420.0 : c_kb);
-      const int n_epi = kWarps - kUnpackWarp0 - 4 * p.unpack_groups;
-      const double t_d = 730.0 * ((p.n_tok / 16 + n_epi / 4 - 1) / (n_epi / 4)) + 1400.0;
+      // straddled tile), which is exposed when the accumulator is single-buffered.
       const bool dbuf = p.n_tok <= kDbufMaxTok;  // double-buffered accumulators: only the last drain of a CTA is exposed
       const long long waves = (tiles + grid - 1) / grid;
-      const double t_dw = t_d;
-      const double cost_whole = (double)waves * p.k_units * t_u + (dbuf ? 1.0 : (double)waves) * t_dw;
+      const double cost_whole = (double)waves * p.k_units * t_u_whole + (dbuf ? 1.0 : (double)waves) * t_d;
       const long long segs = (upc_all + p.k_units - 1) / p.k_units + 1;
-      // A CTA of a stream-K schedule publishes one partial tile and finishes another: int32 partials (2x the bytes of the
-      // fp16 output) go through L2 both ways, the publisher's fence + announcement costs ~5 k cycles after its drain and
-      // the finisher can only start when the slowest contributor has announced.  Measured end to end (profiles/r02/call_m):
-      // ~10 k cycles + 40 per token on top of the plain drain — (128, 4096, 4096) took 23.0 us as stream-K over 148 CTAs
-      // against 10.7 us as 32 whole tiles, while (128, 8192, 21760) wins 29.0 vs 33.3 us because it saves 54 k-blocks per CTA.
-      const double t_fix = 10000.0 + 40.0 * p.n_tok;
       const double cost_split = (double)upc_all * t_u + (dbuf ? 1.0 : (double)segs) * t_d + t_fix;
       if (env_split == 1 || cost_split < cost_whole) {
         a_tiles = tiles;

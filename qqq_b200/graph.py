@@ -73,6 +73,47 @@ class GraphedCallable:
         return self.static_out
 
 
+class PipelinedRunner:
+    """Steps whose input arrives in pinned host memory and whose result goes back to host memory, software-pipelined over two
+    captured graphs: the host-to-device copy of step i+1 and the device-to-host copy of step i-1 run on their own streams
+    under the kernels of step i (one copy engine per direction), so that a serving loop pays the PCIe time of a step only
+    where it exceeds the step's compute.  Every step still copies its own input in and its own result out."""
+
+    def __init__(self, fn, example_input: torch.Tensor, warmup: int = 2):
+        dev = example_input.device
+        self.g = [GraphedCallable(fn, example_input, warmup), GraphedCallable(fn, example_input, warmup)]
+        self.s_in, self.s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        mk = lambda: [torch.cuda.Event(), torch.cuda.Event()]  # noqa: E731
+        self.ev_in, self.ev_done, self.ev_out = mk(), mk(), mk()
+        self.i = 0
+        self.dev = dev
+
+    def step(self, x_host: torch.Tensor, out_host: torch.Tensor) -> None:
+        """Enqueue one step: x_host (pinned) -> device -> graph -> out_host (pinned).  Asynchronous; `drain()` joins."""
+        b = self.i & 1
+        g = self.g[b]
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_in.wait_event(self.ev_done[b])  # the step that last read this input buffer has finished
+        with torch.cuda.stream(self.s_in):
+            g.static_in.copy_(x_host, non_blocking=True)
+            self.ev_in[b].record(self.s_in)
+        cur.wait_event(self.ev_in[b])
+        cur.wait_event(self.ev_out[b])  # this graph's previous result has left its static output
+        g.graph.replay()
+        self.ev_done[b].record(cur)
+        self.s_out.wait_event(self.ev_done[b])
+        with torch.cuda.stream(self.s_out):
+            out_host.copy_(g.static_out, non_blocking=True)
+            self.ev_out[b].record(self.s_out)
+        self.i += 1
+
+    def drain(self) -> None:
+        """Make the current stream wait for every copy issued so far (call before timing / before reading results)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for e in self.ev_out + self.ev_in:
+            cur.wait_event(e)
+
+
 def capture(fn, example_input: torch.Tensor, warmup: int = 2) -> GraphedCallable:
     """Capture `fn(example_input)` (any composition of QuantLinear / qqq_gemm / dynamic_quant calls)."""
     return GraphedCallable(fn, example_input, warmup)

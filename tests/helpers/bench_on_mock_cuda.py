@@ -62,6 +62,11 @@ class GC:
 qg.GraphedCallable = GC
 qg.capture = lambda fn, x, warmup=2: GC(fn, x)
 qg.fork_join = lambda thunks: [t() for t in thunks]  # no streams on the mock surface
+class PR:
+    def __init__(s, fn, x, warmup=2): s.fn, s.x, s.i = fn, x.clone(), 0
+    def step(s, x_host, out_host): s.x.copy_(x_host); out_host.copy_(s.fn(s.x)); s.i += 1
+    def drain(s): pass
+qg.PipelinedRunner = PR
 src = open(os.path.join(ROOT, "bench.py")).read()
 src = src.replace('dev = f"cuda:{local_rank}"', 'dev = "cpu"')
 src = src.replace('dist.init_process_group("nccl", device_id=torch.device(dev))', 'dist.init_process_group("gloo")')

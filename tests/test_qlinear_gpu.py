@@ -116,3 +116,22 @@ def test_fork_join_branches_give_the_serial_bits_in_a_graph():
     x2 = x * 0.5
     assert torch.equal(g(x2), serial(x2))
     assert all(int(m.workspace.abs().sum()) == 0 for m in mods)
+
+
+def test_pipelined_runner_overlaps_copies_without_mixing_steps():
+    """graph.PipelinedRunner: H2D of step i+1 / D2H of step i-1 on their own streams around two alternating graphs — every
+    step must deliver the result of ITS OWN input."""
+    from qqq_b200 import graph
+
+    p = O.make_problem(64, 1024, 512, -1, seed=12)
+    ql = _module(p, 1024, 512, -1)
+    xs = [(torch.from_numpy(p["x"]) * (0.25 * (i + 1))).half().pin_memory() for i in range(6)]
+    want = [ql(x.cuda()).cpu() for x in xs]
+    outs = [torch.empty(64, 512, dtype=torch.float16).pin_memory() for _ in xs]
+    r = graph.PipelinedRunner(lambda t: ql(t), xs[0].cuda())
+    for x, o in zip(xs, outs):
+        r.step(x, o)
+    r.drain()
+    torch.cuda.synchronize()
+    for w, o in zip(want, outs):
+        assert torch.equal(w, o)
