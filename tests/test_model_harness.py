@@ -286,3 +286,43 @@ def test_rtn_quantizers_take_s_extra_from_the_stored_fp16_weight_like_the_refere
     s_extra = q[3]
     assert s_extra.dtype == torch.float32
     assert np.array_equal(s_extra.numpy(), g["s_extra_fp16_layer"])
+
+
+@pytest.mark.parametrize("cache", [False, True])
+def test_fused_model_and_quant_cache_under_inference_mode(oracle_backend, cache):
+    """tensors created under torch.inference_mode() have no version counter (`x._version` raises); the merged-GEMM
+    cache and the activation-quant cache must work there (serving stacks run under inference_mode) and still never serve a
+    stale entry."""
+    m = qmodel.quantize_model_rtn(tiny_model("llama"), -1)
+    ids = torch.randint(0, 128, (1, 6), generator=torch.Generator().manual_seed(11))
+    ids2 = torch.randint(0, 128, (1, 6), generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        want, want2 = m(input_ids=ids, use_cache=False).logits.clone(), m(input_ids=ids2, use_cache=False).logits.clone()
+    qmodel.fuse_qkv_gate_up(m)
+    qqq_b200.set_act_quant_cache(cache)
+    try:
+        with torch.inference_mode():
+            got = m(input_ids=ids, use_cache=False).logits
+            got2 = m(input_ids=ids2, use_cache=False).logits
+            got3 = m(input_ids=ids, use_cache=False).logits
+    finally:
+        qqq_b200.set_act_quant_cache(False)
+    assert torch.equal(got, want) and torch.equal(got2, want2) and torch.equal(got3, want)
+
+
+def test_shared_gemm_never_serves_an_entry_left_by_an_interrupted_forward(oracle_backend):
+    """a forward interrupted between q_proj and v_proj leaves the merged output cached; the next forward starts
+    at slot 0 again, which always recomputes — also when the new input sits at the same address with the same version."""
+    ql = [qqq_b200.QuantLinear(4, -1, 128, n, bias=False) for n in (64, 64, 128)]
+    for i, q in enumerate(ql):
+        g = torch.Generator().manual_seed(i)
+        q.B = torch.randint(-2**31, 2**31 - 1, q.B.shape, dtype=torch.int32, generator=g)
+        q.s_channel = torch.full_like(q.s_channel, 1e-3)
+    shared = qmodel._SharedGemm(qqq_b200.merge_quant_linears(ql))
+    x = torch.randn(3, 128).half()
+    first = shared.slice(x, 0).clone()  # "q_proj" only: the forward is interrupted here
+    x.data.copy_(torch.randn(3, 128).half())  # same storage, same address; `.data` does not bump the version
+    again = shared.slice(x, 0)
+    assert not torch.equal(first, again)
+    assert torch.equal(again, ql[0](x)) and torch.equal(shared.slice(x, 1), ql[1](x)) and torch.equal(shared.slice(x, 2), ql[2](x))
+    assert shared._out is None and shared._ref is None  # every consumer served: references dropped
