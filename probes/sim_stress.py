@@ -1,8 +1,7 @@
 """Long run of the intra-CTA protocol model (tests/pipeline_sim.py) on a library's planner: more shapes, SM counts, CTAs and
 seeds than the CPU suite affords (dev tooling; 10-20 min on one host core).
 
-    python probes/sim_stress.py qqq_b200/libqqq_b200.so              # the default build (pairs modelled with both CTAs)
-    python probes/sim_stress.py VARIANT.so helpers                   # a -DQQQ_DRAIN_HELPERS build (probes/build_variant.py)
+    python probes/sim_stress.py qqq_b200/libqqq_b200.so [seeds]      # pairs are modelled with both CTAs on one clock
 """
 import ctypes
 import os
@@ -16,8 +15,7 @@ from test_pipeline_sim import SHAPES  # noqa: E402
 from test_schedule import KEYS  # noqa: E402
 
 lib = ctypes.CDLL(os.path.abspath(sys.argv[1]))
-helpers = len(sys.argv) > 2 and sys.argv[2] == "helpers"
-seeds = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+seeds = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 lib.qqq_b200_plan.argtypes = [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_int)]
 lib.qqq_b200_plan.restype = ctypes.c_int
 
@@ -40,10 +38,10 @@ for (M, N, K, gs) in SHAPES + extra:
                 continue
             for seed in range(seeds):
                 if p["pair"]:
-                    PairSim(p, cta, M, seed=seed, helpers=helpers)
+                    PairSim(p, cta, M, seed=seed)
                     n_pair += 1
                 else:
-                    CtaSim(p, cta, M, seed=seed, helpers=helpers).run()
+                    CtaSim(p, cta, M, seed=seed).run()
                 n += 1
-print(f"simulated {n} CTA runs ({n_pair} of them CTA pairs, helpers={helpers}): all finished, all parity waits exact, "
+print(f"simulated {n} CTA runs ({n_pair} of them CTA pairs): all finished, all parity waits exact, "
       "all chunks drained once")

@@ -9,8 +9,7 @@ latencies and warp interleavings, and checks what a GPU run can only show as a h
     barrier's current phase bit differs from p, so a waiter that is a whole phase behind passes on stale data (the
     round-1 weight-ring bug: ring depth not a multiple of the unpack-group ownership period) and one that is a phase ahead
     hangs; the model asserts `completed_phases == intended_phase + 1` at every pass;
-  * every 16-token chunk of every accumulator is drained exactly once, also with the drain-helper variant
-    (-DQQQ_DRAIN_HELPERS: unpack warps take a share of the drain, see drain_share in the kernel).
+  * every 16-token chunk of every accumulator is drained exactly once.
 
 Cross-CTA split-K waits are not modelled (publishers never wait, so they cannot close a cycle).  CTA pairs
 (cta_group::2): `PairSim` runs both CTAs on one clock — own weight rings, unpack and epilogue warps, half of the token
@@ -71,13 +70,11 @@ class Deadlock(AssertionError):
 
 
 class CtaSim:
-    def __init__(self, plan, cta, M, seed=0, helpers=False, dbuf_max_tok=208, twin=False, leader=None):
+    def __init__(self, plan, cta, M, seed=0, dbuf_max_tok=208, twin=False, leader=None):
         """twin=True: CTA pair approximated by doubling this CTA's arrivals on the shared barriers.
         leader=<CtaSim>: this object is the PEER CTA (rank 1) of a faithfully modelled pair (see PairSim)."""
-        self.p, self.rng, self.helpers = plan, (leader.rng if leader else random.Random(seed)), helpers
+        self.p, self.rng = plan, (leader.rng if leader else random.Random(seed))
         self.leader, self.seed = leader, seed
-        self.hinfo = {}  # dbuf -> segment whose ticket the epilogue has handed to the unpack warps
-        self.helper_done = {}  # unpack warp -> number of segments whose hand-off it has consumed
         self.segs = segments(plan, cta)
         self.KU, self.KSUB, self.G = plan["k_units"], plan["ksub"], plan["unpack_groups"]
         self.NSW, self.NST = plan["stages_w"], plan["stages_t"]
@@ -91,8 +88,7 @@ class CtaSim:
         self.fullw, self.emptyw = mk("fullw", self.NSW, 1), mk("emptyw", self.NSW, 4 * self.KSUB)
         self.fullt, self.emptyt = mk("fullt", self.NST, 1), mk("emptyt", self.NST, 1)
         self.afull, self.aempty = mk("afull", K_MAX_A_SLOTS, 4 * self.KSUB * self.pair), mk("aempty", K_MAX_A_SLOTS, 1)
-        n_dempty = (self.n_epi + (4 * self.G if helpers else 0)) * self.pair
-        self.dfull, self.dempty = mk("dfull", 2, 1), mk("dempty", 2, n_dempty)
+        self.dfull, self.dempty = mk("dfull", 2, 1), mk("dempty", 2, self.n_epi * self.pair)
         self.clock = leader.clock if leader else {"t": 0, "seq": 0, "events": []}  # shared by the CTAs of a pair
         self.peer = None
         if leader is not None:
@@ -103,7 +99,7 @@ class CtaSim:
             for b in leader.afull:
                 b.count = b.pending = 4 * self.KSUB * 2
             for b in leader.dempty:
-                b.count = b.pending = (self.n_epi + (4 * self.G if helpers else 0)) * 2
+                b.count = b.pending = self.n_epi * 2
             self.fullt, self.afull, self.dempty = leader.fullt, leader.afull, leader.dempty
         self.drained = {}  # (segment, quadrant, chunk) -> count
         self.units = [(sg, kb) for sg, (_, kb0, kb1) in enumerate(self.segs) for kb in range(kb0, kb1)]
@@ -177,9 +173,6 @@ class CtaSim:
         CTAs (ticket); the model draws it once per segment so that every role of the CTA sees the same answer."""
         return self.whole(sg) or random.Random(hash((id(self.p) & 0xFFFF, self.seed, sg))).random() < 0.5
 
-    def helped(self, sg):
-        return self.helpers and self.finisher(sg) and (self.ndbuf == 1 or sg == len(self.segs) - 1)
-
     def drain(self, sg, q, first_chunk, step):
         rows = self.seg_rows(sg)
         for mb in range(16 * first_chunk, rows, 16 * step):
@@ -190,28 +183,7 @@ class CtaSim:
     def unpack_warp(self, grp, q):
         st, as_ = Ring(self.NSW), Ring(self.NA)
         turn = 0
-        h = {"seg": 0, "end": (self.segs[0][2] - self.segs[0][1]) if self.segs else 0}
-        self.helper_done[(grp, q)] = 0
-
-        def drain_due(u):
-            while h["seg"] < len(self.segs) and h["end"] - 1 + self.NA <= u:
-                sg = h["seg"]
-                dbuf, use = sg % self.ndbuf, sg // self.ndbuf
-                yield ("wait", self.dfull[dbuf], use & 1, use)
-                if not self.whole(sg):  # spin on misc[2 + dbuf] until the epilogue has published this segment's ticket
-                    while self.hinfo.get(dbuf) != sg:
-                        yield ("sleep", self.rng.randint(5, 50))
-                if self.helped(sg):
-                    yield from self.drain(sg, q, self.n_epi // 4 + grp, 4)
-                self.dempty[dbuf].arrive(self.pair)
-                h["seg"] += 1
-                self.helper_done[(grp, q)] = h["seg"]
-                if h["seg"] < len(self.segs):
-                    h["end"] += self.segs[h["seg"]][2] - self.segs[h["seg"]][1]
-
         for u in range(len(self.units)):
-            if self.helpers:
-                yield from drain_due(u)
             stage_ready = slot_ready = False
             for _sub in range(self.KSUB):
                 if turn == grp:
@@ -227,8 +199,6 @@ class CtaSim:
                 turn = 0 if turn == self.G - 1 else turn + 1
             st.advance()
             as_.advance()
-        if self.helpers:
-            yield from drain_due(1 << 30)
 
     def epilogue_warp(self, e):
         q, eh = e % 4, e // 4
@@ -240,17 +210,11 @@ class CtaSim:
                     # ticket; the finisher also waits until the other contributors' partials are published (other CTAs,
                     # never blocked by this one)
                     yield ("sleep", self.rng.randint(20, 2000 if self.finisher(sg) else 100))
-                    if self.helpers:
-                        prev = self.hinfo.get(dbuf)
-                        assert prev is None or all(v > prev for v in self.helper_done.values()), (
-                            "ticket word overwritten before every unpack warp had read it")
-                        self.hinfo[dbuf] = sg
                     self.ticket_ready = sg
                 else:  # named barrier of the epilogue warps around the ticket
                     while getattr(self, "ticket_ready", -1) < sg:
                         yield ("sleep", self.rng.randint(5, 50))
-            step = 4 if self.helped(sg) else self.n_epi // 4
-            yield from self.drain(sg, q, eh, step)
+            yield from self.drain(sg, q, eh, self.n_epi // 4)
             self.dempty[dbuf].arrive(self.pair)
 
     # ---- scheduler ------------------------------------------------------------------------------------------------
@@ -322,9 +286,9 @@ class CtaSim:
                     assert self.drained.get((sg, q, c), 0) == 1, f"segment {sg} quadrant {q} chunk {c}: drained {self.drained.get((sg, q, c), 0)}x"
 
 
-def PairSim(plan, cta, M, seed=0, helpers=False, dbuf_max_tok=208):
+def PairSim(plan, cta, M, seed=0, dbuf_max_tok=208):
     """Both CTAs of a pair (cluster of 2, cta_group::2) on one clock: each has its own weight ring and unpack / epilogue
     warps and loads half of the token tile; the leader's MMA warp consumes both and its commits release both."""
-    lead = CtaSim(plan, cta, M, seed=seed, helpers=helpers, dbuf_max_tok=dbuf_max_tok)
-    peer = CtaSim(plan, cta, M, seed=seed, helpers=helpers, dbuf_max_tok=dbuf_max_tok, leader=lead)
+    lead = CtaSim(plan, cta, M, seed=seed, dbuf_max_tok=dbuf_max_tok)
+    peer = CtaSim(plan, cta, M, seed=seed, dbuf_max_tok=dbuf_max_tok, leader=lead)
     return lead.run(extra_roles=peer.roles("peer:"))

@@ -108,3 +108,62 @@ def test_decode_plan_hides_the_fixup():
     for cta in range(p["grid"]):
         segs = segments(p, cta)
         assert segs[-1][1:] == (0, p["k_units"])
+
+
+def _check_plan(M, N, K, gs, sms, max_par):
+    """All invariants the kernel relies on, for one problem (same checks as above, caller's max_par honoured)."""
+    out = (ctypes.c_int * 20)()
+    assert _lib.load().qqq_b200_plan(M, N, K, gs, sms, max_par, out) == 0
+    p = dict(zip(KEYS, out))
+    pair = p["pair"]
+    assert pair in (0, 1) and (pair == 0 or (p["n_tiles"] % 2 == 0 and p["n_tok"] % 32 == 0 and p["grid"] % 2 == 0)), p
+    KU, tiles = p["k_units"], p["m_tiles"] * (p["n_tiles"] >> pair)
+    assert p["n_tiles"] == -(-N // 128) and p["k_blocks"] == -(-K // 128)
+    assert p["a_tiles"] + p["b_tiles"] == tiles and p["a_units"] == p["a_tiles"] * KU and p["a_upc"] >= 1, p
+    assert 1 <= p["grid"] <= sms, p
+    grid = p["grid"] >> pair
+    assert p["n_tok"] % 16 == 0 and 16 <= p["n_tok"] <= 256, p
+    assert (p["m_tiles"] - 1) * p["n_tok"] < M <= p["m_tiles"] * p["n_tok"], p  # no empty token tile
+    assert p["ksub"] in (1, 2, 4) and KU == -(-p["k_blocks"] // p["ksub"]), p
+    assert p["smem_bytes"] <= 232448 and 2 <= p["stages_w"] <= 16 and 2 <= p["stages_t"] <= 16, p
+    acc_cols = (2 if p["n_tok"] <= 208 else 1) * p["n_tok"]
+    assert (512 - acc_cols) // (32 * p["ksub"]) >= 2, p
+    G, ks = p["unpack_groups"], p["ksub"]
+    assert G in (2, 3) and p["stages_w"] % (1 if ks >= G else G // math.gcd(ks, G)) == 0, p
+    assert p["b_step"] == grid, p
+    count, contributors = {}, {}
+    for cta in range(grid):
+        for (t, kb0, kb1) in segments(dict(p, grid=grid), cta):
+            assert 0 <= t < tiles and 0 <= kb0 < kb1 <= KU, (p, cta, t, kb0, kb1)
+            for kb in range(kb0, kb1):
+                count[(t, kb)] = count.get((t, kb), 0) + 1
+            contributors.setdefault(t, []).append(cta)
+    assert len(count) == tiles * KU and all(v == 1 for v in count.values()), p
+    tile_ints, split = p["n_tok"] * 128, False
+    for t, ctas in contributors.items():
+        if len(ctas) > 1:
+            split = True
+            parts = (t * KU + KU - 1) // p["a_upc"] - (t * KU) // p["a_upc"] + 1
+            assert t < p["a_tiles"] and parts == len(ctas) < 65536, p  # tickets live in 16 bits of the lock word
+            last_block = (parts - 2) * (p["a_tiles"] << pair) + (t << pair) + pair
+            assert (last_block + 1) * tile_ints <= 64 * max_par * N, ("partial tiles do not fit C", p)
+    if split:
+        assert (tiles << pair) <= (N // 128) * max_par, ("not enough lock words in workspace", p)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_planner_random_shapes(seed):
+    """1000 random (M, N, K, groupsize, SM count, max_par) problems per seed, ragged in every dimension the boundary
+    allows (N % 64, K % 128, any M, any grid cap, the caller's scratch down to max_par = 1).  24,000 more were run once
+    with other seeds while writing this test (no violation)."""
+    import random
+
+    rnd = random.Random(seed)
+    edge_m = [1, 2, 7, 16, 17, 31, 32, 33, 48, 63, 64, 65, 100, 127, 128, 129, 200, 255, 256, 257, 300, 511, 512, 513,
+              1000, 1024, 1025, 2000, 2048, 4096, 5000, 8192]
+    for _ in range(1000):
+        M = rnd.choice(edge_m + [rnd.randint(1, 9000)])
+        N = 64 * rnd.choice([1, 2, 3, 4, 5, 7, 8, 9, 16, 17, 31, 32, 33, 43, 64, 86, 128, 170, 172, 224, 340, rnd.randint(1, 400)])
+        K = 128 * rnd.choice([1, 2, 3, 4, 5, 7, 8, 9, 11, 16, 28, 32, 43, 64, 86, 112, 170, rnd.randint(1, 200)])
+        _check_plan(M, N, K, rnd.choice([-1, 128]), rnd.choice([1, 2, 3, 4, 7, 8, 37, 64, 100, 132, 147, 148, rnd.randint(1, 148)]),
+                    rnd.choice([1, 2, 4, 8, 16, 16, 16, 16, 32]))
