@@ -18,7 +18,7 @@
 //                              fragment, so the weight tile becomes the UMMA A operand in TMEM without any
 //                              shuffle, shared-memory round trip or load-time repack.
 //   warp 1  MMA issuer       : tcgen05.mma.cta_group::1.kind::i8, A from TMEM, B (tokens) from a smem descriptor,
-//                              int32 accumulators in TMEM (double-buffered when n_tok <= kDbufMaxTok = 192)
+//                              int32 accumulators in TMEM (double-buffered when n_tok <= kDbufMaxTok = 208)
 //   4-8 epilogue warps       : tcgen05.ld -> fp32 * s2[n] * s1[m] (reference order, :695-700) -> fp16 -> D
 //
 // The two smem rings are decoupled: weight stages are released by the unpack warps as soon as they are in
