@@ -43,7 +43,8 @@ extern "C" {
  *
  * thread_k, thread_n, sms: -1 = auto.  thread_k/thread_n are validated like the reference
  * (csrc/qqq_gemm.cu:867-916) and otherwise ignored: this kernel has its own tiling.  sms caps the grid.
- * Alignment: A, B, D, s3 16-byte aligned; K % 128 == 0 and N % 64 == 0 (reference: (K%64,N%128)|(K%128,N%64)).
+ * Alignment: A, B, D, s3 16-byte aligned.  Shapes: the reference's rule, (K % 128 == 0 and N % 64 == 0) or (K % 64 == 0 and
+ * N % 128 == 0) (csrc/qqq_gemm.cu:847-865,899-916); per-group additionally K % 128 == 0.  Any M >= 0.
  * The launch goes to `stream` on device `dev` (a device guard is applied; the reference has none).
  */
 int qqq_gemm_sm100a(const void* A, const void* B, void* C, void* D, const void* s1, const void* s2,

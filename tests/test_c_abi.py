@@ -74,3 +74,43 @@ def test_missing_library_is_a_loud_error(monkeypatch, tmp_path):
     monkeypatch.delenv("QQQ_B200_LIB")
     monkeypatch.setattr(_lib, "_lib", None)
     _lib.load()
+
+
+C_CLIENT = r"""
+/* A host written in plain C99 binding the boundary exactly as include/qqq_b200.h declares it. */
+#include <stdio.h>
+#include <string.h>
+#include "qqq_b200.h"
+
+int main(void) {
+  int plan[20];
+  if (qqq_b200_version() < 100) return 10;
+  /* configs[4], M = 1024: pure host planning, no GPU needed */
+  if (qqq_b200_plan(1024, 21760, 8192, -1, 148, 16, plan) != QQQ_OK) return 11;
+  if (plan[0] < 1 || plan[0] > 148 || plan[1] % 16 != 0 || plan[3] != 170 || plan[4] != 64) return 12;
+  /* the reference's return codes (csrc/qqq_gemm.cu:947-948) come back before any CUDA call */
+  if (qqq_gemm_sm100a(NULL, NULL, NULL, NULL, NULL, NULL, NULL, 4, 100, 128, NULL, -1, 0, NULL, -1, -1, -1, 16) !=
+      QQQ_ERR_PROB_SHAPE) return 13;
+  if (strlen(qqq_b200_last_error()) == 0) return 14;
+  if (qqq_gemm_sm100a(NULL, NULL, NULL, NULL, NULL, NULL, NULL, 4, 128, 256, NULL, 64, 0, NULL, -1, -1, -1, 16) !=
+      QQQ_ERR_KERN_SHAPE) return 15;
+  if (qqq_gemm_bias_sm100a(NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, 128, 128, NULL, -1, 0, NULL, -1, 16) != QQQ_OK)
+    return 16; /* empty problem: silent no-op like the reference (:1002-1003) */
+  if (qqq_act_quant_strided_sm100a(NULL, 128, NULL, NULL, 0, 128, 0, NULL) != QQQ_OK) return 17;
+  printf("grid=%d n_tok=%d launches=%lld\n", plan[0], plan[1], qqq_b200_launch_count());
+  return 0;
+}
+"""
+
+
+def test_plain_c_host_compiles_links_and_calls(tmp_path):
+    """The header is C (not C++-only) and a C host can bind every kind of entry point: gcc -std=c99 -pedantic -Werror."""
+    _lib.load()
+    src = tmp_path / "client.c"
+    src.write_text(C_CLIENT)
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(str(_lib.LIB_PATH))
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lqqq_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert out.startswith("grid=") and "launches=" in out
